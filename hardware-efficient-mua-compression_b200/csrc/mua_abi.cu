@@ -1,0 +1,404 @@
+// C ABI of libmua_b200.so (see include/mua_b200.h): argument validation + kernel launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "mua_calibrate.cuh"
+#include "mua_decode.cuh"
+#include "mua_dropin.cuh"
+#include "mua_encode.cuh"
+
+using namespace mua;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) { return fail(MUA_E_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
+
+#define CHECK_LAUNCH(what)                                   \
+    do {                                                     \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what); \
+    } while (0)
+
+#define REQUIRE(cond, ...)                                    \
+    do {                                                      \
+        if (!(cond)) return fail(MUA_E_INVALID, __VA_ARGS__); \
+    } while (0)
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_layout(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C) {
+    REQUIRE(d_sym != nullptr, "d_sym is NULL");
+    REQUIRE(aligned16(d_sym), "d_sym must be 16-byte aligned");
+    REQUIRE(C >= 0, "C < 0");
+    REQUIRE(T >= 0 && T <= (1 << 28), "T out of range [0, 2^28]");
+    if (!d_off) REQUIRE(stride % 16 == 0 && stride >= (int64_t)((T + 15) & ~15), "stride must be a multiple of 16 and >= round_up(T,16)");
+    (void)d_len;
+    return MUA_OK;
+}
+
+void layout_sizes(int S, int K, int Lmax, TabHdr* h) {
+    h->S = S;
+    h->K = K;
+    h->Lmax = Lmax;
+    h->W = dec_window_bits(S, K, Lmax);
+    h->enc1_off = align_up((int)sizeof(TabHdr), 128);
+    h->enc2_off = align_up(h->enc1_off + S * K * 16 * 4, 128);
+    h->dec_off = align_up(h->enc2_off + S * K * 256 * 8, 128);
+    h->total_bytes = align_up(h->dec_off + ((S * K) << h->W) * 8, 128);
+}
+
+template <int S>
+void launch_calibrate(const CalibParams& P, cudaStream_t st) {
+    const int grid = (P.L.C + CAL_WARPS - 1) / CAL_WARPS;
+    k_calibrate<S><<<grid, CAL_WARPS * 32, 0, st>>>(P);
+}
+
+int dispatch_calibrate(const CalibParams& P, cudaStream_t st) {
+    if (P.L.C == 0) return MUA_OK;
+    switch (P.S) {
+        case 2: launch_calibrate<2>(P, st); break;
+        case 3: launch_calibrate<3>(P, st); break;
+        case 4: launch_calibrate<4>(P, st); break;
+        case 5: launch_calibrate<5>(P, st); break;
+        case 6: launch_calibrate<6>(P, st); break;
+        case 7: launch_calibrate<7>(P, st); break;
+        case 8: launch_calibrate<8>(P, st); break;
+        case 9: launch_calibrate<9>(P, st); break;
+        case 10: launch_calibrate<10>(P, st); break;
+        default: return fail(MUA_E_INVALID, "S=%d outside 2..10", P.S);
+    }
+    CHECK_LAUNCH("k_calibrate");
+    return MUA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mua_abi_version(void) { return MUA_ABI_VERSION; }
+const char* mua_last_error(void) { return g_err; }
+
+int mua_canonical_codebook(const uint8_t* h_lens, int K, int S, uint16_t* h_codes_out) {
+    REQUIRE(h_lens && h_codes_out, "NULL argument");
+    REQUIRE(S >= 2 && S <= MUA_MAX_S && K >= 1 && K <= MUA_MAX_K, "S/K out of range");
+    for (int k = 0; k < K; ++k) {
+        const uint8_t* L = h_lens + (size_t)k * S;
+        uint32_t code = 0;
+        for (int r = 0; r < S; ++r) {
+            REQUIRE(L[r] >= 1 && L[r] <= 15, "length out of range");
+            if (r) {
+                REQUIRE(L[r] >= L[r - 1], "rows must be ascending (SCLV)");
+                code = (code + 1) << (L[r] - L[r - 1]);
+            }
+            REQUIRE(code < (1u << L[r]), "row %d is not a valid prefix code (Kraft sum > 1)", k);
+            h_codes_out[(size_t)k * S + r] = (uint16_t)code;
+        }
+    }
+    return MUA_OK;
+}
+
+size_t mua_tables_bytes(int S, int K) {
+    if (S < 2 || S > MUA_MAX_S || K < 1 || K > MUA_MAX_K) return 0;
+    TabHdr h;
+    layout_sizes(S, K, 9, &h);   // worst-case window so the size does not depend on the rows
+    TabHdr h2;
+    layout_sizes(S, K, 1, &h2);
+    return (size_t)(h.total_bytes > h2.total_bytes ? h.total_bytes : h2.total_bytes);
+}
+
+int mua_build_tables(void* d_tables, const uint8_t* h_lens, const uint16_t* h_codes, int S, int K, void* stream) {
+    REQUIRE(d_tables && h_lens && h_codes, "NULL argument");
+    REQUIRE(aligned16(d_tables), "d_tables must be 16-byte aligned");
+    REQUIRE(S >= 2 && S <= MUA_MAX_S && K >= 1 && K <= MUA_MAX_K, "S/K out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    TabHdr h;
+    memset(&h, 0, sizeof(h));
+    int Lmax = 0;
+    for (int k = 0; k < K; ++k) {
+        double kraft = 0;
+        for (int r = 0; r < S; ++r) {
+            int L = h_lens[(size_t)k * S + r];
+            REQUIRE(L >= 1 && L <= 9, "codeword length %d outside 1..9", L);
+            REQUIRE(h_codes[(size_t)k * S + r] < (1u << L), "codeword wider than its length");
+            h.lens[k][r] = (uint8_t)L;
+            h.codes[k][r] = h_codes[(size_t)k * S + r];
+            kraft += 1.0 / (double)(1u << L);
+            if (L > Lmax) Lmax = L;
+        }
+        REQUIRE(kraft == 1.0, "row %d is not Kraft-complete (decode LUT needs a complete prefix code)", k);
+        for (int a = 0; a < S; ++a)
+            for (int b = 0; b < S; ++b) {
+                if (a == b) continue;
+                int la = h.lens[k][a], lb = h.lens[k][b];
+                if (la <= lb) REQUIRE((h.codes[k][b] >> (lb - la)) != h.codes[k][a], "row %d is not prefix-free", k);
+            }
+    }
+    layout_sizes(S, K, Lmax, &h);
+    cudaError_t e = cudaMemcpyAsync(d_tables, &h, sizeof(h), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "upload table header");
+    k_build_tables<<<S * K, 256, 0, st>>>(reinterpret_cast<uint8_t*>(d_tables));
+    CHECK_LAUNCH("k_build_tables");
+    // the header lives on this stack frame: make sure the (pageable) upload has been consumed
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "build tables");
+    return MUA_OK;
+}
+
+int mua_bin_raster(const void* d_raster, int dtype, int64_t T0, int32_t C, int32_t bin_res, int64_t* d_counts, uint8_t* d_sym,
+                   int64_t sym_stride, int32_t S, void* stream) {
+    REQUIRE(d_raster, "d_raster is NULL");
+    REQUIRE(T0 >= 0 && C >= 0 && bin_res >= 1, "bad T0/C/bin_res");
+    REQUIRE(d_counts || d_sym, "no output requested");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = (T0 + bin_res - 1) / bin_res;
+    if (nb == 0 || C == 0) return MUA_OK;
+    if (d_counts) {
+        dim3 grid((C + 255) / 256, (unsigned)(nb < 32768 ? nb : 32768));
+        switch (dtype) {
+            case MUA_DT_U8: k_bin_counts<uint8_t, unsigned long long><<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_counts); break;
+            case MUA_DT_I32: k_bin_counts<int32_t, long long><<<grid, 256, 0, st>>>((const int32_t*)d_raster, T0, C, bin_res, nb, d_counts); break;
+            case MUA_DT_I64: k_bin_counts<int64_t, long long><<<grid, 256, 0, st>>>((const int64_t*)d_raster, T0, C, bin_res, nb, d_counts); break;
+            case MUA_DT_F32: k_bin_counts<float, float><<<grid, 256, 0, st>>>((const float*)d_raster, T0, C, bin_res, nb, d_counts); break;
+            case MUA_DT_F64: k_bin_counts<double, double><<<grid, 256, 0, st>>>((const double*)d_raster, T0, C, bin_res, nb, d_counts); break;
+            default: return fail(MUA_E_INVALID, "unknown dtype %d", dtype);
+        }
+        CHECK_LAUNCH("k_bin_counts");
+    }
+    if (d_sym) {
+        REQUIRE(dtype == MUA_DT_U8, "symbol output needs a uint8 raster");
+        REQUIRE(S == 0 || (S >= 2 && S <= MUA_MAX_S), "S outside {0, 2..10}");
+        REQUIRE(sym_stride >= nb, "sym_stride < number of bins");
+        REQUIRE(nb <= (int64_t)65535 * BIN_TB, "too many bins for one launch");
+        dim3 grid((C + BIN_TC - 1) / BIN_TC, (unsigned)((nb + BIN_TB - 1) / BIN_TB));
+        const bool al = aligned16(d_sym) && (sym_stride % 16 == 0);
+        k_bin_sym<<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_sym, al ? sym_stride : sym_stride, S ? S - 1 : 255);
+        CHECK_LAUNCH("k_bin_sym");
+    }
+    return MUA_OK;
+}
+
+int mua_calibrate(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C, int32_t S,
+                  const int32_t* h_H, int32_t nH, int32_t use_sort, int32_t window_mode, const void* d_tables, uint32_t active_lo,
+                  uint32_t active_hi, int32_t* d_cutoff, int32_t* d_end, uint8_t* d_peak, uint8_t* d_enc, int32_t* d_assign_m,
+                  int32_t* d_post_m, int64_t* d_bits, int64_t* d_nsym, void* stream) {
+    int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
+    if (rc) return rc;
+    REQUIRE(S >= 2 && S <= MUA_MAX_S, "S=%d outside 2..10", S);
+    REQUIRE(h_H && nH >= 1 && nH <= MUA_MAX_H, "nH outside 1..%d", MUA_MAX_H);
+    REQUIRE(window_mode >= 0 && window_mode <= 2, "bad window_mode");
+    REQUIRE(d_tables, "d_tables is NULL");
+    CalibParams P;
+    memset(&P, 0, sizeof(P));
+    P.L = Layout{d_sym, d_off, d_len, stride, T, C};
+    P.S = S; P.nH = nH; P.use_sort = use_sort; P.mode = window_mode; P.train = 0;
+    for (int i = 0; i < nH; ++i) P.H[i] = h_H[i];
+    P.tab = reinterpret_cast<const TabHdr*>(d_tables);
+    P.active = ((unsigned long long)active_hi << 32) | active_lo;
+    REQUIRE(P.active != 0, "no active SCLV row");
+    P.cutoff = d_cutoff; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
+    P.assign_m = d_assign_m; P.post_m = d_post_m; P.bits = d_bits; P.nsym = d_nsym;
+    return dispatch_calibrate(P, (cudaStream_t)stream);
+}
+
+int mua_train_hist(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C, int32_t S,
+                   int32_t* d_hist_sorted, void* stream) {
+    int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
+    if (rc) return rc;
+    REQUIRE(S >= 2 && S <= MUA_MAX_S, "S=%d outside 2..10", S);
+    REQUIRE(d_hist_sorted, "d_hist_sorted is NULL");
+    CalibParams P;
+    memset(&P, 0, sizeof(P));
+    P.L = Layout{d_sym, d_off, d_len, stride, T, C};
+    P.S = S; P.nH = 1; P.use_sort = 0; P.mode = MUA_WINDOW_NONE; P.train = 1;
+    P.H[0] = 0x7FFFFFFF;
+    P.active = 1;
+    P.train_hist = d_hist_sorted;
+    return dispatch_calibrate(P, (cudaStream_t)stream);
+}
+
+int mua_select_sclv(const int32_t* d_hist, int64_t N, const void* d_tables, uint32_t active_lo, uint32_t active_hi, uint8_t* d_enc,
+                    int64_t* d_min1, int64_t* d_min2, void* stream) {
+    REQUIRE(d_hist && d_tables && d_enc, "NULL argument");
+    REQUIRE(N >= 0, "N < 0");
+    const unsigned long long active = ((unsigned long long)active_hi << 32) | active_lo;
+    REQUIRE(active != 0, "no active SCLV row");
+    if (N == 0) return MUA_OK;
+    const int grid = (int)((N + 255) / 256 < (int64_t)sm_count() * 8 ? (N + 255) / 256 : (int64_t)sm_count() * 8);
+    k_select<<<grid, 256, 0, (cudaStream_t)stream>>>(d_hist, N, reinterpret_cast<const TabHdr*>(d_tables), active, d_enc, d_min1, d_min2);
+    CHECK_LAUNCH("k_select");
+    return MUA_OK;
+}
+
+int mua_bit_counts(const int32_t* d_hist, const uint8_t* d_enc, int64_t N, const void* d_tables, int64_t* d_bits, int64_t* d_nsym,
+                   void* stream) {
+    REQUIRE(d_hist && d_enc && d_tables && d_bits && d_nsym, "NULL argument");
+    REQUIRE(N >= 0, "N < 0");
+    if (N == 0) return MUA_OK;
+    const int grid = (int)((N + 255) / 256 < (int64_t)sm_count() * 8 ? (N + 255) / 256 : (int64_t)sm_count() * 8);
+    k_bit_counts<<<grid, 256, 0, (cudaStream_t)stream>>>(d_hist, d_enc, N, reinterpret_cast<const TabHdr*>(d_tables), d_bits, d_nsym);
+    CHECK_LAUNCH("k_bit_counts");
+    return MUA_OK;
+}
+
+int mua_elim_scores(const uint8_t* d_enc, const int64_t* d_min1, const int64_t* d_min2, int64_t N, int32_t K, int64_t* d_assign_hist,
+                    int64_t* d_score, void* stream) {
+    REQUIRE(d_enc && d_min1 && d_min2 && d_assign_hist && d_score, "NULL argument");
+    REQUIRE(K >= 1 && K <= MUA_MAX_K && N >= 0, "bad K/N");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_assign_hist, 0, sizeof(int64_t) * K, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_score, 0, sizeof(int64_t) * K, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    if (N == 0) return MUA_OK;
+    const int grid = (int)((N + 255) / 256 < (int64_t)sm_count() * 4 ? (N + 255) / 256 : (int64_t)sm_count() * 4);
+    k_elim_scores<<<grid, 256, 0, st>>>(d_enc, d_min1, d_min2, N, K, reinterpret_cast<unsigned long long*>(d_assign_hist),
+                                        reinterpret_cast<unsigned long long*>(d_score));
+    CHECK_LAUNCH("k_elim_scores");
+    return MUA_OK;
+}
+
+int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C, int32_t S,
+               const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak, const uint8_t* d_enc, const void* d_tables,
+               int32_t K, int32_t Lmax, uint8_t* d_stream, int64_t slot_bytes, uint32_t* d_chunk_off, int32_t chunk_stride,
+               int64_t* d_total_bits, int32_t* d_overflow, void* stream) {
+    int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
+    if (rc) return rc;
+    REQUIRE(d_start && d_end && d_peak && d_enc && d_tables && d_stream && d_chunk_off && d_total_bits && d_overflow, "NULL argument");
+    REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
+    REQUIRE(chunk_stride >= (T + TILE - 1) / TILE && chunk_stride >= 1, "chunk_stride < ceil(T/%d)", TILE);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 0) return MUA_OK;
+    REQUIRE(S >= 2 && S <= MUA_MAX_S && K >= 1 && K <= MUA_MAX_K && Lmax >= 1 && Lmax <= 9, "bad S/K/Lmax");
+    TabHdr h;
+    layout_sizes(S, K, Lmax, &h);
+    EncParams P;
+    P.L = Layout{d_sym, d_off, d_len, stride, T, C};
+    P.S = S; P.start = d_start; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
+    P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax;
+    P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
+    P.total_bits = d_total_bits; P.overflow = d_overflow;
+    const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
+    if (h.Lmax <= 2) {
+        constexpr int RW = 128;
+        const int smem = EncSmem<RW>::PER_WARP * ENC_WARPS;
+        cudaError_t e = cudaFuncSetAttribute(k_encode<RW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");
+        const int grid = ctas_needed < sm_count() * 4 ? ctas_needed : sm_count() * 4;
+        k_encode<RW, true><<<grid, ENC_WARPS * 32, smem, st>>>(P);
+    } else {
+        constexpr int RW = 512;
+        const int smem = EncSmem<RW>::PER_WARP * ENC_WARPS;
+        cudaError_t e = cudaFuncSetAttribute(k_encode<RW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");
+        const int grid = ctas_needed < sm_count() * 3 ? ctas_needed : sm_count() * 3;
+        k_encode<RW, false><<<grid, ENC_WARPS * 32, smem, st>>>(P);
+    }
+    CHECK_LAUNCH("k_encode");
+    return MUA_OK;
+}
+
+int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off, int32_t chunk_stride, const int64_t* d_off,
+               int64_t stride, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
+               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, uint8_t* d_dec, void* stream) {
+    REQUIRE(d_stream && d_chunk_off && d_start && d_end && d_peak && d_enc && d_tables && d_dec, "NULL argument");
+    REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
+    REQUIRE(aligned16(d_dec), "d_dec must be 16-byte aligned");
+    REQUIRE(d_off || stride % 16 == 0, "stride must be a multiple of 16");
+    REQUIRE(chunk_stride >= 1 && C >= 0, "bad chunk_stride/C");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 0) return MUA_OK;
+    REQUIRE(S >= 2 && S <= MUA_MAX_S && K >= 1 && K <= MUA_MAX_K && Lmax >= 1 && Lmax <= 9, "bad S/K/Lmax");
+    TabHdr h;
+    layout_sizes(S, K, Lmax, &h);
+    DecParams P;
+    P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
+    P.off = d_off; P.stride = stride; P.C = C; P.S = S; P.start = d_start; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
+    P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax; P.dec = d_dec;
+    const long long items = (long long)C * chunk_stride;
+    const long long blocks_needed = (items + DEC_THREADS - 1) / DEC_THREADS;
+    const int lut_bytes = ((h.S * h.K) << h.W) * 8;
+    if (lut_bytes <= 64 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut_bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+        const long long cap = (long long)sm_count() * 8;
+        k_decode<true><<<(int)(blocks_needed < cap ? blocks_needed : cap), DEC_THREADS, lut_bytes, st>>>(P);
+    } else {
+        const long long cap = (long long)sm_count() * 16;
+        k_decode<false><<<(int)(blocks_needed < cap ? blocks_needed : cap), DEC_THREADS, 0, st>>>(P);
+    }
+    CHECK_LAUNCH("k_decode");
+    return MUA_OK;
+}
+
+int mua_verify(const uint8_t* d_sym, const uint8_t* d_dec, const int64_t* d_off, int64_t stride, int32_t C, int32_t S,
+               const int32_t* d_start, const int32_t* d_end, unsigned long long* d_mismatch, void* stream) {
+    REQUIRE(d_sym && d_dec && d_start && d_end && d_mismatch, "NULL argument");
+    REQUIRE(S >= 2 && S <= MUA_MAX_S && C >= 0, "bad S/C");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_mismatch, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    if (C == 0) return MUA_OK;
+    const int grid = (C + 7) / 8 < sm_count() * 8 ? (C + 7) / 8 : sm_count() * 8;
+    k_verify<<<grid, 256, 0, st>>>(d_sym, d_dec, d_off, stride, C, S, d_start, d_end, d_mismatch);
+    CHECK_LAUNCH("k_verify");
+    return MUA_OK;
+}
+
+int mua_online_histogram(uint8_t* d_x, int64_t n, int64_t H, int32_t max_firing_rate, uint32_t* d_counts, int32_t* d_first,
+                         void* stream) {
+    REQUIRE(d_x && d_counts && d_first, "NULL argument");
+    REQUIRE(n >= 1, "empty input (the reference raises IndexError, functions_1.py:45)");
+    REQUIRE(max_firing_rate >= 0 && max_firing_rate <= 255, "max_firing_rate outside 0..255");
+    k_online_hist<<<1, 256, 0, (cudaStream_t)stream>>>(d_x, n, H, max_firing_rate, d_counts, d_first);
+    CHECK_LAUNCH("k_online_hist");
+    return MUA_OK;
+}
+
+int mua_approx_sort(const void* d_hist, int dtype, int32_t n, int64_t count, int64_t* d_idx, void* stream) {
+    REQUIRE(d_hist && d_idx, "NULL argument");
+    REQUIRE(n >= 1 && count >= 0, "bad n/count");
+    if (count == 0) return MUA_OK;
+    const int grid = (int)((count + 127) / 128);
+    if (dtype == MUA_DT_I64) k_approx_sort<long long><<<grid, 128, 0, (cudaStream_t)stream>>>((const long long*)d_hist, n, count, d_idx);
+    else if (dtype == MUA_DT_F64) k_approx_sort<double><<<grid, 128, 0, (cudaStream_t)stream>>>((const double*)d_hist, n, count, d_idx);
+    else return fail(MUA_E_INVALID, "histogram dtype must be int64 or float64");
+    CHECK_LAUNCH("k_approx_sort");
+    return MUA_OK;
+}
+
+int mua_synth(uint8_t* d_sym, int64_t stride, int32_t T, int32_t C, int64_t c0, uint32_t seed, const uint32_t* d_thr, int32_t bursty,
+              void* stream) {
+    REQUIRE(d_sym && d_thr, "NULL argument");
+    REQUIRE(aligned16(d_sym) && stride % 16 == 0 && stride >= (int64_t)((T + 15) & ~15), "stride must be a multiple of 16 and >= round_up(T,16)");
+    REQUIRE(T >= 0 && C >= 0, "bad T/C");
+    if (T == 0 || C == 0) return MUA_OK;
+    const long long total = (long long)C * ((T + 15) / 16);
+    const long long cap = (long long)sm_count() * 16;
+    const long long need = (total + 255) / 256;
+    k_synth<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(d_sym, stride, T, C, c0, seed, d_thr, bursty);
+    CHECK_LAUNCH("k_synth");
+    return MUA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// Stages 2-4: windowed histograms (one scan per channel for all history lengths), approx-sort peak
+// and rank map, SCLV cost + first-argmin selection, bit counts.  Also: train histograms, stand-alone
+// selection, elimination-round scores, table build.
+#pragma once
+#include "mua_common.cuh"
+
+namespace mua {
+
+// ---------------------------------------------------------------------------------------------
+// table build: one CTA per (peak p, codebook row k)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob) {
+    TabHdr* T = reinterpret_cast<TabHdr*>(blob);
+    const int S = T->S, K = T->K, W = T->W;
+    const int p = blockIdx.x / K, k = blockIdx.x % K;
+    const int tid = threadIdx.x;
+    __shared__ uint8_t s_rank[16], s_idx[16], s_len[16];
+    __shared__ uint16_t s_code[16];
+    if (tid < 16) {
+        int s = tid < S ? tid : S - 1;
+        int r = rank_of(p, s, S);
+        s_rank[tid] = (uint8_t)r;              // raw nibble -> rank (saturation folded in)
+        s_len[tid] = tid < S ? T->lens[k][tid] : 0;
+        s_code[tid] = tid < S ? T->codes[k][tid] : 0;
+    }
+    __syncthreads();
+    if (tid < S) s_idx[s_rank[tid]] = (uint8_t)tid;
+    __syncthreads();
+    if (k == 0 && tid < 16) {
+        T->rank[p][tid] = s_rank[tid];
+        T->idx[p][tid] = tid < S ? s_idx[tid] : 0;
+    }
+    uint32_t* enc1 = reinterpret_cast<uint32_t*>(blob + T->enc1_off) + (size_t)(p * K + k) * 16;
+    uint2* enc2 = reinterpret_cast<uint2*>(blob + T->enc2_off) + (size_t)(p * K + k) * 256;
+    unsigned long long* dec = reinterpret_cast<unsigned long long*>(blob + T->dec_off) + ((size_t)(p * K + k) << W);
+    if (tid < 16) enc1[tid] = ((uint32_t)s_len[s_rank[tid]] << 16) | s_code[s_rank[tid]];
+    {
+        int r0 = s_rank[tid & 15], r1 = s_rank[tid >> 4];
+        uint32_t l1 = s_len[r1];
+        enc2[tid] = make_uint2(((uint32_t)s_code[r0] << l1) | s_code[r1], (uint32_t)s_len[r0] + l1);
+    }
+    for (int v = tid; v < (1 << W); v += blockDim.x) {
+        unsigned long long e = 0;
+        int used = 0, n = 0;
+        while (n < DEC_MAX_SYM) {
+            int hit = -1;
+            for (int r = 0; r < S; ++r) {
+                int l = s_len[r];
+                if (used + l <= W && (uint32_t)((v >> (W - used - l)) & ((1 << l) - 1)) == s_code[r]) { hit = r; break; }
+            }
+            if (hit < 0) break;
+            e |= (unsigned long long)s_idx[hit] << (8 * n);
+            used += s_len[hit];
+            ++n;
+        }
+        e |= (unsigned long long)(n | (used << 4)) << 56;
+        dec[v] = e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// calibrate: warp per channel
+// ---------------------------------------------------------------------------------------------
+struct CalibParams {
+    Layout L;
+    int32_t S, nH, use_sort, mode, train;
+    int32_t H[MUA_MAX_H];
+    const TabHdr* tab;
+    unsigned long long active;
+    int32_t* cutoff;
+    int32_t* end;
+    uint8_t* peak;
+    uint8_t* enc;
+    int32_t* assign_m;
+    int32_t* post_m;
+    int64_t* bits;
+    int64_t* nsym;
+    int32_t* train_hist;
+};
+
+constexpr int CAL_WARPS = 4;
+constexpr int CAL_TILE = 512;   // bytes per warp step (16 B per lane)
+
+template <int S>
+__global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_constant__ CalibParams P) {
+    __shared__ int s_bnd[CAL_WARPS][2 * MUA_MAX_H];
+    __shared__ int s_snap[CAL_WARPS][2 * MUA_MAX_H][S];   // [boundary][v] = #{t < b : x_t >= v}, v = 1..S-1
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * CAL_WARPS + warp;
+    if (c >= P.L.C) return;
+    const int nH = P.nH, nB = 2 * nH;
+    const int n = ch_len(P.L, c);
+    const uint8_t* row = P.L.sym + ch_off(P.L, c);
+
+    // boundaries: cutoffs then window ends (0 = unused)
+    if (lane < nH) {
+        int H = P.H[lane];
+        int cut = n > 0 ? min(max(H, 1), n) : 0;
+        int end = 0;
+        if (P.mode == MUA_WINDOW_SKIP) {
+            end = cut + n / 2;
+            if (end > n) end = -1;
+        } else if (P.mode == MUA_WINDOW_TRUNCATE) {
+            end = min(cut + n / 2, n);
+        }
+        s_bnd[warp][lane] = cut;
+        s_bnd[warp][nH + lane] = end;
+    }
+    for (int i = lane; i < nB * S; i += 32) (&s_snap[warp][0][0])[i] = 0;
+    __syncwarp();
+    int scan_end = 0;
+    for (int i = 0; i < nB; ++i) scan_end = max(scan_end, s_bnd[warp][i]);
+
+    int acc[S];
+#pragma unroll
+    for (int v = 0; v < S; ++v) acc[v] = 0;
+    const int rd_end = (n + 15) & ~15;   // rows are readable up to round_up(len, 16)
+    for (int t0 = 0; t0 < scan_end; t0 += CAL_TILE) {
+        const int p0 = t0 + lane * 16;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (p0 < rd_end) q = *reinterpret_cast<const uint4*>(row + p0);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t lo7[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lo7[j] = w[j] & 0x7F7F7F7Fu;
+        // boundaries inside (t0, t0 + CAL_TILE]
+        for (int bi = 0; bi < nB; ++bi) {
+            const int b = s_bnd[warp][bi];
+            if (b > t0 && b <= t0 + CAL_TILE) {
+                const int nvalid = min(max(b - p0, 0), 16);
+                uint32_t m[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int nb = min(max(nvalid - 4 * j, 0), 4);
+                    m[j] = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+                }
+#pragma unroll
+                for (int v = 1; v < S; ++v) {
+                    int part = acc[v];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) part += __popc(ge_mask(w[j], lo7[j], v) & m[j]);
+                    part = warp_sum(part);
+                    if (lane == 0) s_snap[warp][bi][v] = part;
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 1; v < S; ++v) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[v] += __popc(ge_mask(w[j], lo7[j], v));
+        }
+    }
+    __syncwarp();
+
+    // ---- epilogue: lane h handles history length h ----
+    if (lane >= nH) return;
+    const int h = lane;
+    const TabHdr* T = P.tab;
+    const int cut = s_bnd[warp][h];
+    const int end = s_bnd[warp][nH + h];
+    int hist[S], post[S];
+    {
+        int g_prev = cut;   // G_0 = number of samples
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            int g_next = s + 1 < S ? s_snap[warp][h][s + 1] : 0;
+            hist[s] = g_prev - g_next;
+            g_prev = g_next;
+        }
+    }
+    const bool has_post = end > 0 && P.mode != MUA_WINDOW_NONE;
+    {
+        int g_prev = has_post ? end - cut : 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            int g_next = (has_post && s + 1 < S) ? s_snap[warp][nH + h][s + 1] - s_snap[warp][h][s + 1] : 0;
+            post[s] = g_prev - g_next;
+            g_prev = g_next;
+        }
+    }
+    const size_t o = (size_t)c * nH + h;
+    if (P.train) {
+        // np.flip(np.sort(hist)): descending (get_BR_no_sort.py:147)
+#pragma unroll
+        for (int i = 1; i < S; ++i) {
+#pragma unroll
+            for (int j = S - 1; j >= i; --j) {
+                int a = hist[j - 1], b = hist[j];
+                hist[j - 1] = max(a, b);
+                hist[j] = min(a, b);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) P.train_hist[o * S + s] = hist[s];
+        return;
+    }
+    int p = 0;
+    if (P.use_sort) {   // np.argmax: lowest index on ties (functions_1.py:77)
+        int best = hist[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s)
+            if (hist[s] > best) { best = hist[s]; p = s; }
+    }
+    int am[S], pm[S];   // mapped histograms: m[rank[s]] = hist[s]
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int r = T->rank[p][s];
+#pragma unroll
+        for (int rr = 0; rr < S; ++rr)
+            if (rr == r) { am[rr] = hist[s]; pm[rr] = post[s]; }
+    }
+    long long best_cost = 0;
+    int enc = -1;
+    for (int k = 0; k < T->K; ++k) {
+        if (!((P.active >> k) & 1ull)) continue;
+        long long cost = 0;
+#pragma unroll
+        for (int r = 0; r < S; ++r) cost += (long long)am[r] * T->lens[k][r];
+        if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
+    }
+    if (enc < 0) enc = 0;
+    long long bits = 0, ns = 0;
+#pragma unroll
+    for (int r = 0; r < S; ++r) { bits += (long long)pm[r] * T->lens[enc][r]; ns += pm[r]; }
+    if (P.cutoff) P.cutoff[o] = cut;
+    if (P.end) P.end[o] = (P.mode == MUA_WINDOW_NONE) ? cut : end;
+    if (P.peak) P.peak[o] = (uint8_t)p;
+    if (P.enc) P.enc[o] = (uint8_t)enc;
+    if (P.bits) P.bits[o] = bits;
+    if (P.nsym) P.nsym[o] = ns;
+    if (P.assign_m) {
+#pragma unroll
+        for (int r = 0; r < S; ++r) P.assign_m[o * S + r] = am[r];
+    }
+    if (P.post_m) {
+#pragma unroll
+        for (int r = 0; r < S; ++r) P.post_m[o * S + r] = pm[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone selection / bit counts / elimination scores (thread per histogram)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_select(const int32_t* __restrict__ hist, int64_t N, const TabHdr* __restrict__ T,
+                                                unsigned long long active, uint8_t* __restrict__ enc,
+                                                int64_t* __restrict__ min1, int64_t* __restrict__ min2) {
+    __shared__ uint8_t s_len[MUA_MAX_K][16];
+    for (int i = threadIdx.x; i < MUA_MAX_K * 16; i += blockDim.x) (&s_len[0][0])[i] = (&T->lens[0][0])[i];
+    __syncthreads();
+    const int S = T->S, K = T->K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        int hv[MUA_MAX_S];
+#pragma unroll
+        for (int s = 0; s < MUA_MAX_S; ++s) hv[s] = s < S ? hist[i * S + s] : 0;
+        long long m1 = 0, m2 = 0;
+        int e = -1, cnt = 0;
+        for (int k = 0; k < K; ++k) {
+            if (!((active >> k) & 1ull)) continue;
+            long long cost = 0;
+#pragma unroll
+            for (int r = 0; r < MUA_MAX_S; ++r) cost += (long long)hv[r] * s_len[k][r];
+            if (cnt == 0) { m1 = cost; e = k; }
+            else if (cost < m1) { m2 = m1; m1 = cost; e = k; }
+            else if (cnt == 1 || cost < m2) { m2 = cost; }
+            ++cnt;
+        }
+        if (cnt < 2) m2 = m1;
+        enc[i] = (uint8_t)(e < 0 ? 0 : e);
+        if (min1) min1[i] = m1;
+        if (min2) min2[i] = m2;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bit_counts(const int32_t* __restrict__ hist, const uint8_t* __restrict__ enc, int64_t N,
+                                                    const TabHdr* __restrict__ T, int64_t* __restrict__ bits,
+                                                    int64_t* __restrict__ nsym) {
+    const int S = T->S;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = enc[i];
+        long long b = 0, n = 0;
+        for (int r = 0; r < S; ++r) {
+            int hv = hist[i * S + r];
+            b += (long long)hv * T->lens[k][r];
+            n += hv;
+        }
+        bits[i] = b;
+        nsym[i] = n;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_elim_scores(const uint8_t* __restrict__ enc, const int64_t* __restrict__ min1,
+                                                     const int64_t* __restrict__ min2, int64_t N, int K,
+                                                     unsigned long long* __restrict__ assign_hist,
+                                                     unsigned long long* __restrict__ score) {
+    __shared__ unsigned long long s_delta[MUA_MAX_K], s_cnt[MUA_MAX_K], s_tot;
+    if (threadIdx.x < MUA_MAX_K) { s_delta[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_tot = 0;
+    __syncthreads();
+    unsigned long long tot = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        int e = enc[i];
+        tot += (unsigned long long)min1[i];
+        atomicAdd(&s_delta[e], (unsigned long long)(min2[i] - min1[i]));
+        atomicAdd(&s_cnt[e], 1ull);
+    }
+    atomicAdd(&s_tot, tot);
+    __syncthreads();
+    if (threadIdx.x < K) {
+        atomicAdd(&score[threadIdx.x], s_tot + s_delta[threadIdx.x]);
+        atomicAdd(&assign_hist[threadIdx.x], s_cnt[threadIdx.x]);
+    }
+}
+
+}  // namespace mua

@@ -1,0 +1,116 @@
+// Shared device helpers and the device table block of the MUA compression path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mua_b200.h"
+
+namespace mua {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int TILE = MUA_CHUNK;        // symbols per warp tile == decode chunk
+constexpr int DEC_MAX_SYM = 7;         // symbols per decode-LUT entry (bytes 0..6)
+
+// ---- device table block (built by k_build_tables) ------------------------------------------
+// enc1 : uint32 [S][K][16]    raw nibble b -> (len << 16 | code) of rank[p][min(b,S-1)]
+// enc2 : uint2  [S][K][256]   raw nibble pair (b0 | b1<<4), b0 first in time -> {code, len}
+// dec  : uint64 [S][K][1<<W]  W-bit window -> bytes 0..6 symbols, byte 7 = n | used_bits << 4
+struct TabHdr {
+    int32_t S, K, Lmax, W;
+    int32_t enc1_off, enc2_off, dec_off, total_bytes;
+    uint8_t lens[MUA_MAX_K][16];     // SCLV rows (Stored_SCLVs_S_<S>.pkl), ascending lengths
+    uint16_t codes[MUA_MAX_K][16];   // codeword of rank r
+    uint8_t rank[MUA_MAX_S][16];     // rank[p][s]: approx_sort permutation for peak p (functions_1.py:75-90)
+    uint8_t idx[MUA_MAX_S][16];      // idx[p][r] = symbol of rank r (what approx_sort returns)
+};
+
+__host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// decode window width: wide window while the whole LUT set stays small, else the minimum
+__host__ __device__ inline int dec_window_bits(int S, int K, int Lmax) {
+    if (S * K <= 6) return 10;
+    return Lmax > 8 ? Lmax : 8;
+}
+
+// Closed form of approx_sort's permutation (functions_1.py:75-90).
+// `p > len(hist)/2` is a true division in the reference (:78)  <=>  2p > S.
+__host__ __device__ inline int rank_of(int p, int s, int S) {
+    if (2 * p > S) {
+        int d = S - 1 - p;
+        if (s >= p) return 2 * (s - p);
+        if (s >= p - d) return 2 * (p - s) - 1;
+        return S - 1 - s;
+    }
+    if (s < p) return 2 * (p - s) - 1;
+    if (s <= 2 * p) return 2 * (s - p);
+    return s;
+}
+
+struct Layout {
+    const uint8_t* sym;
+    const int64_t* off;
+    const int32_t* len;
+    int64_t stride;
+    int32_t T;
+    int32_t C;
+};
+__device__ __forceinline__ int64_t ch_off(const Layout& L, int c) { return L.off ? L.off[c] : (int64_t)c * L.stride; }
+__device__ __forceinline__ int ch_len(const Layout& L, int c) { return L.len ? L.len[c] : L.T; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier + TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP) ----------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    uint32_t a = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// bytes >= v  ->  bit 7 of that byte (SWAR threshold compare, any byte value 0..255, 1 <= v <= 127)
+__device__ __forceinline__ uint32_t ge_mask(uint32_t w, uint32_t lo7, int v) {
+    return ((lo7 + (uint32_t)(0x80 - v) * 0x01010101u) | w) & 0x80808080u;
+}
+
+// counter-based RNG of the synthetic generator (mirrors oracle/mua_oracle.py:_mix32)
+__host__ __device__ inline uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+
+}  // namespace mua

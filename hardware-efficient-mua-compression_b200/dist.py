@@ -1,0 +1,44 @@
+"""Channel-sharded multi-GPU plumbing (one process per GPU, torch.distributed).
+
+Channels are independent units (per-channel state is cutoff, peak/rank map, chosen SCLV), so every
+rank runs the whole pipeline on a contiguous block of channels with no data-path collective; only the
+per-channel report (bit count, symbol count, chosen SCLV, peak) is gathered -- one all_gather of a
+packed int64 [n, 4] tensor over NCCL/NVLink (gloo on CPU in the tests).  BR float math is done on the
+host over the gathered array in global channel order (np.mean is order sensitive)."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(C, rank, world):
+    """Contiguous channel block [lo, hi) of `rank`; blocks differ by at most one channel."""
+    return (C * rank) // world, (C * (rank + 1)) // world
+
+
+def gather_channel_report(bits, nsym, enc, peak, C_total, group=None):
+    """All ranks receive int64 [C_total, 4] = (bits, nsym, enc, peak) in global channel order."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local = torch.stack([bits.to(torch.int64), nsym.to(torch.int64), enc.to(torch.int64), peak.to(torch.int64)], dim=1)
+    if world == 1:
+        assert local.shape[0] == C_total
+        return local
+    sizes = [shard_range(C_total, r, world)[1] - shard_range(C_total, r, world)[0] for r in range(world)]
+    rank = dist.get_rank(group)
+    assert local.shape[0] == sizes[rank], "local shard does not match shard_range()"
+    m = max(sizes)
+    padded = torch.zeros((m, 4), dtype=torch.int64, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((world * m, 4), dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * m: r * m + sizes[r]] for r in range(world)], dim=0)
+
+
+def br_report(report, BP):
+    """Host-side BR report from a gathered report tensor: per-channel average bits/symbol and the
+    chosen-system mean BR = np.mean(avg) / (BP/1000) (test_chosen_system.py:121-125)."""
+    r = report.cpu().numpy()
+    with np.errstate(all="ignore"):
+        avg = r[:, 0].astype(np.float64) / r[:, 1].astype(np.float64)
+        return {"avg_bits_per_symbol": avg, "BR": np.mean(avg) / (BP / 1000),
+                "total_bits": int(r[:, 0].sum()), "total_symbols": int(r[:, 1].sum()),
+                "enc": r[:, 2].astype(np.uint8), "peak": r[:, 3].astype(np.uint8)}

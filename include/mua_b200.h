@@ -1,0 +1,188 @@
+/*
+ * mua_b200.h -- C ABI of the B200-native MUA compression hot path (libmua_b200.so).
+ *
+ * Drop-in boundary for the reference's `Compressing data/functions_1.py` path
+ * (zhengzhang96/Hardware-efficient-MUA-compression).  The reference has no FFI of its own (it is
+ * plain Python/NumPy); these entry points are what a ctypes binding for that path binds, one per
+ * stage of the path.  Each declaration cites the reference lines it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `d_*` pointer is DEVICE memory owned by the caller, every
+ *     `h_*` pointer is HOST memory.  No hidden allocation, no retained state between calls.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it; nothing synchronises the device.
+ *   - return value: 0 = ok, <0 = error (MUA_E_*); mua_last_error() returns a thread-local message.
+ *   - re-entrant across distinct streams/devices.
+ *
+ * Channel layout ("recording"): symbols are uint8, one row per channel:
+ *     channel c occupies d_sym[off(c) .. off(c)+len(c)),  off(c) = d_off ? d_off[c] : c*stride,
+ *     len(c) = d_len ? d_len[c] : T.
+ *   d_sym and every off(c) must be 16-byte aligned and the buffer must be readable up to
+ *   off(c) + round_up(len(c), 16) (rows padded to 16 B) -- the encoder stages rows with TMA bulk copies.
+ *
+ * Stream format (defined by oracle/mua_oracle.py:encode_channel; the Python reference emits no
+ * bitstream): per channel the window [start,end) is saturated to S-1, mapped through the
+ * approx-sort rank map of its calibration peak, coded with codebook row enc(c); codewords are
+ * appended MSB-first, stream bit i lives in byte i/8 at bit 7-(i%8); zero-padded to 128 bits.
+ * Side info: uint32 bit offset of every MUA_CHUNK-symbol chunk, chunks aligned to absolute bin index.
+ */
+#ifndef MUA_B200_H
+#define MUA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUA_ABI_VERSION 1
+#define MUA_CHUNK 1024        /* symbols per decode chunk */
+#define MUA_MAX_S 10          /* symbols per alphabet: 2..10 (get_BR_no_sort.py:104) */
+#define MUA_MAX_K 35          /* candidate SCLVs for S=10 (Stored_SCLVs_S_10.pkl) */
+#define MUA_MAX_H 16          /* history lengths per calibrate call (scripts use 9: 2^2..2^10) */
+
+#define MUA_OK 0
+#define MUA_E_INVALID (-1)    /* bad argument (message says which) */
+#define MUA_E_CUDA (-2)       /* CUDA runtime error (message holds cudaGetErrorString) */
+
+/* window rule for the post-calibration ("to be compressed") window */
+#define MUA_WINDOW_NONE 0     /* calibration only: no post window is scanned */
+#define MUA_WINDOW_SKIP 1     /* end = cutoff + len/2; if end > len the channel is skipped
+                                 (get_BR_no_sort.py:178-183) */
+#define MUA_WINDOW_TRUNCATE 2 /* end = min(cutoff + len/2, len) (test_chosen_system.py:99-103) */
+
+/* raster element types accepted by mua_bin_raster */
+#define MUA_DT_U8 0
+#define MUA_DT_I32 1
+#define MUA_DT_I64 2
+#define MUA_DT_F32 3
+#define MUA_DT_F64 4
+
+int mua_abi_version(void);
+const char* mua_last_error(void);
+
+/* ---- codebooks and lookup tables --------------------------------------------------------- */
+
+/* Canonical Huffman codes for K ascending length rows [K][S] (host helper).  [1,2,2] -> 0,10,11,
+ * the only codeword table in the Python hot path (test_chosen_system.py:26-27). */
+int mua_canonical_codebook(const uint8_t* h_lens, int K, int S, uint16_t* h_codes_out);
+
+/* Bytes of the device table block for alphabet size S with K codebook rows. */
+size_t mua_tables_bytes(int S, int K);
+
+/* Build the device table block: SCLV lengths (Stored_SCLVs_S_<S>.pkl rows, get_BR_no_sort.py:119-124),
+ * codewords, and for every (peak p, row k): encode LUTs (saturate + approx_sort rank map
+ * functions_1.py:75-90 + codeword) and the multi-symbol decode LUT. */
+int mua_build_tables(void* d_tables, const uint8_t* h_lens, const uint16_t* h_codes, int S, int K,
+                     void* stream);
+
+/* ---- stage 1: binning --------------------------------------------------------------------- */
+
+/* bin_MUA_data (functions_1.py:11-24): raster [T0][C] (row-major, element type `dtype`) summed over
+ * `bin_res` consecutive rows -> ceil(T0/bin_res) bins, last bin partial.
+ *   d_counts : int64 [nb][C] (reference layout/dtype) or NULL
+ *   d_sym    : uint8 [C][sym_stride] channel-major symbols saturated at S-1 (saturation
+ *              get_BR_no_sort.py:143,164), or NULL; S = 0 means clamp at 255 only. */
+int mua_bin_raster(const void* d_raster, int dtype, int64_t T0, int32_t C, int32_t bin_res,
+                   int64_t* d_counts, uint8_t* d_sym, int64_t sym_stride, int32_t S, void* stream);
+
+/* ---- stages 2-4: calibration windows, histograms, approx-sort, SCLV selection ------------- */
+
+/* For every channel c and history length H_h (h < nH):
+ *   cutoff = min(max(H,1), len)                          functions_1.py:59-68 (the value callers use)
+ *   assign = bincount(min(x,S-1)[:cutoff])               get_BR_no_sort.py:171
+ *   peak   = first argmax(assign) (0 when use_sort == 0) functions_1.py:77
+ *   end    per `window_mode`; post = bincount(min(x,S-1)[cutoff:end])   get_BR_no_sort.py:178-189
+ *   *_m    = histogram permuted by approx_sort's idx     get_BR_with_approx_sort.py:175-176,193
+ *   enc    = first argmin_k sum_r assign_m[r]*SCLV[k][r] over rows k with bit k of
+ *            active_lo/active_hi set                     get_BR_no_sort.py:252,279
+ *   bits   = sum_r SCLV[enc][r]*post_m[r]; nsym = sum post                  get_BR_no_sort.py:282-287
+ * All outputs are optional (NULL skips), shaped [C][nH] (histograms [C][nH][S]).
+ * d_end receives -1 for a skipped channel (MUA_WINDOW_SKIP). */
+int mua_calibrate(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
+                  int32_t T, int32_t C, int32_t S, const int32_t* h_H, int32_t nH, int32_t use_sort,
+                  int32_t window_mode, const void* d_tables, uint32_t active_lo, uint32_t active_hi,
+                  int32_t* d_cutoff, int32_t* d_end, uint8_t* d_peak, uint8_t* d_enc,
+                  int32_t* d_assign_m, int32_t* d_post_m, int64_t* d_bits, int64_t* d_nsym,
+                  void* stream);
+
+/* Full-recording histogram, exactly sorted descending: np.flip(np.sort(hist))
+ * (get_BR_no_sort.py:140-147).  d_hist_sorted int32 [C][S]. */
+int mua_train_hist(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
+                   int32_t T, int32_t C, int32_t S, int32_t* d_hist_sorted, void* stream);
+
+/* SCLV cost + selection on N histograms int32 [N][S] (np.matmul + np.argmin,
+ * get_BR_no_sort.py:229-236): d_enc[n] = first argmin over active rows; optional d_min1/d_min2 =
+ * smallest and second-smallest cost (for the elimination score, :307-316). */
+int mua_select_sclv(const int32_t* d_hist, int64_t N, const void* d_tables, uint32_t active_lo,
+                    uint32_t active_hi, uint8_t* d_enc, int64_t* d_min1, int64_t* d_min2, void* stream);
+
+/* bits[n] = sum_r SCLV[enc[n]][r]*hist[n][r]; nsym[n] = sum_r hist[n][r] (get_BR_no_sort.py:282-287) */
+int mua_bit_counts(const int32_t* d_hist, const uint8_t* d_enc, int64_t N, const void* d_tables,
+                   int64_t* d_bits, int64_t* d_nsym, void* stream);
+
+/* One greedy-elimination round over N train channels (get_BR_no_sort.py:237-240,307-316):
+ *   d_assign_hist[k] = #channels whose argmin is row k      (int64 [K], zeroed by the call)
+ *   d_score[j]       = sum_n (enc[n]==j ? min2[n] : min1[n]) (int64 [K], zeroed by the call) */
+int mua_elim_scores(const uint8_t* d_enc, const int64_t* d_min1, const int64_t* d_min2, int64_t N,
+                    int32_t K, int64_t* d_assign_hist, int64_t* d_score, void* stream);
+
+/* ---- stage 5: Huffman encode -------------------------------------------------------------- */
+
+/* Encode window [d_start[c], d_end[c]) (d_end <= len; d_end <= d_start encodes nothing) of every
+ * channel with rank map of d_peak[c] and codebook row d_enc[c].
+ *   d_stream      : C slots of `slot_bytes` (multiple of 16); slot c holds the padded stream
+ *   d_chunk_off   : uint32 [C][chunk_stride]; entry j = bit offset of chunk j (see header comment)
+ *   d_total_bits  : int64 [C]  (== SCLV[enc] . mapped post histogram, get_BR_no_sort.py:287)
+ *   d_overflow    : int32 [1], set to 1 when a stream did not fit its slot, 2 when K/Lmax do not
+ *                   match the table block (caller zeroes it)
+ *   K, Lmax       : rows and longest codeword of the table block (as passed to mua_build_tables);
+ *                   host-side launch configuration only, the kernels cross-check them */
+int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
+               int32_t T, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end,
+               const uint8_t* d_peak, const uint8_t* d_enc, const void* d_tables, int32_t K,
+               int32_t Lmax, uint8_t* d_stream, int64_t slot_bytes, uint32_t* d_chunk_off,
+               int32_t chunk_stride, int64_t* d_total_bits, int32_t* d_overflow, void* stream);
+
+/* ---- stage 6: table-driven chunk-parallel decode ------------------------------------------ */
+
+/* Inverse of mua_encode: symbols are written back at their absolute bin index, i.e. d_dec uses the
+ * same layout (d_off/stride) as the input; bytes outside [start,end) are not touched. */
+int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off,
+               int32_t chunk_stride, const int64_t* d_off, int64_t stride, int32_t C, int32_t S,
+               const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
+               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, uint8_t* d_dec,
+               void* stream);
+
+/* Round-trip check on the device: counts positions in [start,end) where d_dec != min(d_sym, S-1).
+ * d_mismatch : uint64 [1] (zeroed by the call). */
+int mua_verify(const uint8_t* d_sym, const uint8_t* d_dec, const int64_t* d_off, int64_t stride,
+               int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end,
+               unsigned long long* d_mismatch, void* stream);
+
+/* ---- the literal functions_1.py signatures (batch-of-1; used by the drop-in module) --------- */
+
+/* online_histogram_w_sat_based_nb_of_samples (functions_1.py:27-68) on one channel of n >= 1 uint8
+ * samples: i = min(max(H,1), n); d_x[:i] is saturated IN PLACE (`>= max_firing_rate`, :45-46);
+ * d_counts[v] (uint32 [256]) = occurrences of value v in d_x[:i]; d_first[v] (int32 [256]) = first
+ * position of v (0x7FFFFFFF if absent) -- the dict's insertion order (:48-53). */
+int mua_online_histogram(uint8_t* d_x, int64_t n, int64_t H, int32_t max_firing_rate,
+                         uint32_t* d_counts, int32_t* d_first, void* stream);
+
+/* approx_sort (functions_1.py:75-90) on `count` histograms of length n (dtype MUA_DT_I64 or
+ * MUA_DT_F64): d_idx int64 [count][n] = rank -> symbol permutation around the first argmax. */
+int mua_approx_sort(const void* d_hist, int dtype, int32_t n, int64_t count, int64_t* d_idx,
+                    void* stream);
+
+/* ---- synthetic MUA (bench/test input; integer-only counter RNG, mirrored by the oracle) ---- */
+
+/* d_sym[c][t] for c in [c0, c0+C): see oracle/mua_oracle.py:synth_symbols.  d_thr: uint32 [256][24]. */
+int mua_synth(uint8_t* d_sym, int64_t stride, int32_t T, int32_t C, int64_t c0, uint32_t seed,
+              const uint32_t* d_thr, int32_t bursty, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUA_B200_H */
