@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- channel-bins/s encoded+decoded of the MUA compression hot path on N B200s.
+
+One "step" = one pass of the hot path (calibrate -> Huffman encode -> chunk-parallel decode) over
+this rank's shard of the cfg5 synthetic stream (BASELINE.json configs[4]: 1M channels x 1 h @ 50 ms
+sharded over 8 GPUs = 125 000 channels x 72 000 bins per GPU, S=3, H=64, codebook 0/10/11);
+weak scaling: every rank processes its own 125k-channel shard, only the per-channel report
+(bits, symbols, SCLV index, peak) is gathered with NCCL inside the step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...          (N > 1)
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU path instead (literal
+port in oracle/ref_port.py on all host cores; the Python reference itself cannot travel to the box)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "channel-bins/s encoded+decoded"
+UNIT = "channel-bins/s"
+S, H, BP, SCLV = 3, 64, 50, (1, 2, 2)
+SEED = 6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--channels", type=int, default=125000, help="channels per GPU")
+    ap.add_argument("--bins", type=int, default=72000, help="bins per channel (1 h at 50 ms)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline leg")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "cfg5 shard: %d channels x %d bins per GPU (1M-channel x 1-hour stream over 8 GPUs), S=3 H=64 BP=50ms, codebook 0/10/11, bursty Poisson" % (a.channels, a.bins)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline legs (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def _cpu_block(args):
+    """worker: literal reference loop on one block of channels; returns (seconds, post-window bins).
+    The synthetic block is generated once per process and cached (outside the timer)."""
+    seed, c0, nch, T, reps = args
+    from oracle import mua_oracle as O, ref_port as R
+    key = (seed, c0, nch, T)
+    if key not in _CPU_CACHE:
+        thr = O.synth_threshold_table(float(BP))
+        _CPU_CACHE[key] = O.synth_symbols(seed, np.arange(c0, c0 + nch), T, thr, True)
+    x = _CPU_CACHE[key]
+    best, nsym = None, 0
+    for _ in range(reps):
+        ch = [x[i].copy() for i in range(nch)]
+        t = time.perf_counter()
+        bits, n = R.chosen_system_loop(ch, S=S, H=H, sclv=SCLV)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+        nsym = int(n.sum())
+    return best, nsym
+
+
+def cpu_baseline_single(T, nch=96):
+    """reference loop on one core: best of 3 on a 96-channel x T slice of the same synthetic stream."""
+    dt, nsym = _cpu_block((SEED, 0, nch, T, 3))
+    return {"value": nsym / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d channels x %d bins of the workload, literal port of test_chosen_system.py:80-106 "
+                      "(oracle/ref_port.py), 1 process, best of 3; counts bits like the reference (no bitstream)" % (nch, T),
+            "host_cores": os.cpu_count()}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    nch = 96
+    ctx = mp.get_context("fork")
+    vals = []
+    with ctx.Pool(cores) as pool:
+        jobs = [(SEED, i * nch, nch, a.bins, 1) for i in range(cores)]
+        for it in range(a.warmup + a.steps):
+            t = time.perf_counter()
+            res = pool.map(_cpu_block, jobs, chunksize=1)
+            wall = time.perf_counter() - t
+            # every core runs the loop on its own block in parallel; step time = slowest worker's loop time
+            slow = max(r[0] for r in res)
+            nsym = sum(r[1] for r in res)
+            if it >= a.warmup:
+                vals.append((nsym / slow, slow, wall))
+    v = float(np.mean([x[0] for x in vals]))
+    ms = float(np.mean([x[1] for x in vals]) * 1e3)
+    sample = ("%d processes x %d channels x %d bins per step, literal port of the reference loop "
+              "(test_chosen_system.py:80-106) in oracle/ref_port.py; synthetic generation outside the timer; "
+              "the reference counts bits from histograms, it emits no bitstream and has no decoder" % (cores, nch, a.bins))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import mua_b200
+    from mua_b200 import pipeline as P, dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    C, T = a.channels, a.bins
+    C_total = C * world
+
+    thr = P.synth_threshold_table(float(BP))
+    rec = P.synth_recording(C, T, seed=SEED, BP_ms=float(BP), bursty=True, c0=rank * C, device=dev, thr=thr)
+    cb = mua_b200.Codebook(S, np.array([SCLV]), device=dev)
+    want = ("cutoff", "end", "peak", "enc", "bits", "nsym")
+    cal = P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=want)
+    slot = cb.worst_case_slot_bytes(T // 2 + 16)
+    es = P.encode(rec, cb, cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0], slot_bytes=slot)
+    dec = torch.zeros_like(rec.sym)
+    torch.cuda.synchronize()
+
+    def step(ev=None):
+        P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=want, out=cal)
+        st, en, pk, ec = cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0]
+        if ev: ev[1].record()
+        P.encode(rec, cb, st, en, pk, ec, out=es)
+        if ev: ev[2].record()
+        P.decode(es, rec, cb, st, en, pk, ec, out=dec)
+        if ev: ev[3].record()
+        rep = None
+        if world > 1:
+            rep = D.gather_channel_report(es.total_bits, cal["nsym"][:, 0], ec, pk, C_total)
+        if ev: ev[4].record()
+        return rep
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
+    t_end = torch.cuda.Event(enable_timing=True)
+    rep = None
+    for k in range(a.steps):
+        evs[k][0].record()
+        rep = step(evs[k])
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    total_ms = evs[0][0].elapsed_time(t_end)
+    stage_ms = np.array([[evs[k][i].elapsed_time(evs[k][i + 1]) for i in range(4)] for k in range(a.steps)]).mean(axis=0)
+    if world > 1:
+        tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        total_ms = float(tmax.item())
+
+    # ---- checks outside the timed region: lossless, stream length == SCLV . histogram ----
+    st, en = cal["cutoff"][:, 0], cal["end"][:, 0]
+    mism = int(P.verify(rec, dec, S, st, en).item())
+    assert mism == 0, "decode is not lossless: %d mismatches" % mism
+    assert int(es.overflow.item()) == 0
+    assert torch.equal(es.total_bits, cal["bits"][:, 0]), "encoded length != SCLV . post histogram"
+    nsym_local = int(cal["nsym"][:, 0].sum().item())
+    bits_local = int(es.total_bits.sum().item())
+    tot = torch.tensor([nsym_local, bits_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    nsym_all, bits_all = int(tot[0].item()), int(tot[1].item())
+    if rep is None:
+        rep = D.gather_channel_report(es.total_bits, cal["nsym"][:, 0], cal["enc"][:, 0], cal["peak"][:, 0], C_total)
+    br = D.br_report(rep, BP) if rank == 0 else None
+
+    ms_per_step = total_ms / a.steps
+    value = nsym_all / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (encode vs decode), algorithmic bytes per launch ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak_gbs, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_chunks = int(((en + 1023) // 1024 - st // 1024).clamp(min=0).sum().item())
+    side = 4 * n_chunks + 8 * C
+    enc_bytes = nsym_local + bits_local / 8 + side            # symbols read + stream written + side info
+    dec_bytes = bits_local / 8 + nsym_local + 4 * n_chunks    # stream read + symbols written + offsets read
+    stages = {"calibrate_ms": float(stage_ms[0]), "encode_ms": float(stage_ms[1]), "decode_ms": float(stage_ms[2]),
+              "gather_ms": float(stage_ms[3]),
+              "encode_gbs": enc_bytes / stage_ms[1] / 1e6, "decode_gbs": dec_bytes / stage_ms[2] / 1e6,
+              "encode_frac": enc_bytes / stage_ms[1] / 1e6 / peak_gbs, "decode_frac": dec_bytes / stage_ms[2] / 1e6 / peak_gbs,
+              "combined_gbs": (enc_bytes + dec_bytes) / (stage_ms[1] + stage_ms[2]) / 1e6,
+              "combined_frac": (enc_bytes + dec_bytes) / (stage_ms[1] + stage_ms[2]) / 1e6 / peak_gbs,
+              "bits_per_symbol": bits_local / max(nsym_local, 1)}
+    dom = "k_encode" if stage_ms[1] >= stage_ms[2] else "k_decode"
+    ach = stages["encode_gbs"] if dom == "k_encode" else stages["decode_gbs"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("channels") == C and tj.get("bins") == T:
+            traffic = tj.get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": enc_bytes if dom == "k_encode" else dec_bytes}
+
+    # ---- e2e: host buffers in, compressed streams + report out, chunked over 3 CUDA streams ----
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, rec, cb, dev, world, rank)
+
+    cpu = cpu_baseline_single(T) if rank == 0 else None
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "channels_per_gpu": C, "bins": T, "total_channels": C_total,
+                       "l2": "inputs (%.1f GB per GPU) are larger than L2" % (C * T / 1e9), "sharding": "channels, contiguous blocks"},
+            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * a.steps,
+            "clocks": clocks, "BR_bits_per_s_per_channel": float(br["BR"]), "lossless": True,
+            "symbols_per_step": nsym_all}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(a, rec, cb, dev, world, rank):
+    """Same metric through the public API with HOST buffers: every step copies the shard's symbols
+    from pinned host memory to the device, runs calibrate/encode/decode, and reads the compressed
+    streams and the per-channel report back to pinned host memory.  Channels are processed in blocks
+    on 3 CUDA streams so copies overlap compute."""
+    import torch
+    import torch.distributed as dist
+    from mua_b200 import pipeline as P
+    C, T = a.channels, a.bins
+    nblk = max(1, min(10, C // 1000))
+    bounds = [(C * i) // nblk for i in range(nblk + 1)]
+    h_in = torch.empty((C, rec.stride), dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(rec.sym)                                   # setup: the host owns the input
+    slot = cb.worst_case_slot_bytes(T // 2 + 16)
+    h_stream = torch.empty((C, slot), dtype=torch.uint8, pin_memory=True)
+    h_rep = torch.empty((C, 2), dtype=torch.int64, pin_memory=True)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+    want = ("cutoff", "end", "peak", "enc", "bits", "nsym")
+    bufs = []
+    maxb = max(bounds[i + 1] - bounds[i] for i in range(nblk))
+    for s in streams:
+        with torch.cuda.stream(s):
+            r = P.Recording(sym=torch.empty((maxb, rec.stride), dtype=torch.uint8, device=dev), C=maxb, T=T, stride=rec.stride)
+            cal = P.calibrate(r, cb, [H], use_sort=True, window="truncate", want=want)
+            es = P.encode(r, cb, cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0], slot_bytes=slot)
+            dec = torch.zeros_like(r.sym)
+            repd = torch.empty((maxb, 2), dtype=torch.int64, device=dev)
+            bufs.append((r, cal, es, dec, repd))
+    torch.cuda.synchronize()
+
+    def one_step():
+        for i in range(nblk):
+            lo, hi = bounds[i], bounds[i + 1]
+            n = hi - lo
+            s = streams[i % 3]
+            r, cal, es, dec, repd = bufs[i % 3]
+            with torch.cuda.stream(s):
+                r.sym[:n].copy_(h_in[lo:hi], non_blocking=True)
+                r.C = n
+                P.calibrate(r, cb, [H], use_sort=True, window="truncate", want=want, out=cal)
+                st, en, pk, ec = cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0]
+                P.encode(r, cb, st, en, pk, ec, out=es)
+                P.decode(es, r, cb, st, en, pk, ec, out=dec)
+                repd[:n, 0] = es.total_bits[:n]
+                repd[:n, 1] = cal["nsym"][:n, 0]
+                h_stream[lo:hi].copy_(es.stream[:n], non_blocking=True)
+                h_rep[lo:hi].copy_(repd[:n], non_blocking=True)
+        for s in streams:
+            s.synchronize()
+
+    one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.e2e_steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.e2e_steps
+    wall_ms = (time.perf_counter() - t0) * 1e3 / a.e2e_steps
+    ms = max(ms, wall_ms)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    nsym = int(h_rep[:, 1].sum().item())
+    tot = torch.tensor([nsym], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    return {"value": int(tot.item()) / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(C * rec.stride),
+            "d2h_bytes_per_step": int(C * slot + C * 16), "ms_per_step": ms, "steps": a.e2e_steps,
+            "api": "mua_b200.pipeline.calibrate/encode/decode (C ABI) on pinned host buffers, %d channel blocks over 3 CUDA streams" % nblk}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

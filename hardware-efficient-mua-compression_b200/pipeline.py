@@ -100,7 +100,7 @@ def _active_words(active, cb):
 
 
 def calibrate(rec: Recording, cb: Codebook, H, use_sort=True, window="skip", active=None,
-              want=("cutoff", "end", "peak", "enc", "assign_m", "post_m", "bits", "nsym")):
+              want=("cutoff", "end", "peak", "enc", "assign_m", "post_m", "bits", "nsym"), out=None):
     """Stages 2-4 for every channel and every history length in H (mua_calibrate).  Returns a dict of
     tensors shaped [C, nH] (histograms [C, nH, S]); see include/mua_b200.h for the reference lines."""
     lib = _lib.load()
@@ -112,7 +112,8 @@ def calibrate(rec: Recording, cb: Codebook, H, use_sort=True, window="skip", act
               "peak": ((rec.C, nH), torch.uint8), "enc": ((rec.C, nH), torch.uint8),
               "assign_m": ((rec.C, nH, cb.S), torch.int32), "post_m": ((rec.C, nH, cb.S), torch.int32),
               "bits": ((rec.C, nH), torch.int64), "nsym": ((rec.C, nH), torch.int64)}
-    out = {k: torch.zeros(shapes[k][0], dtype=shapes[k][1], device=dev) for k in want}
+    if out is None:      # pass a previous result as `out` to reuse its buffers (no allocation in the call)
+        out = {k: torch.zeros(shapes[k][0], dtype=shapes[k][1], device=dev) for k in want}
     hH = (C.c_int32 * nH)(*H)
     lo, hi = _active_words(active, cb)
     g = lambda k: _ptr(out.get(k))

@@ -451,7 +451,8 @@ def synth_symbols(seed: int, channels: np.ndarray, T: int, thr: np.ndarray, burs
     ch = np.asarray(channels, dtype=np.uint32)
     t = np.arange(T, dtype=np.uint32)
     seed32 = np.uint32(seed & 0xFFFFFFFF)
-    cls = (_mix32((seed32 * np.uint32(0x9E3779B9) + ch).astype(np.uint32)) & np.uint32(255)).astype(np.int64)
+    base = np.uint32((int(seed32) * 0x9E3779B9) & 0xFFFFFFFF)
+    cls = (_mix32((base + ch).astype(np.uint32)) & np.uint32(255)).astype(np.int64)
     hc = _mix32(ch ^ np.uint32(0x68E31DA4))
     u = _mix32((hc[:, None] + (t[None, :] * np.uint32(0x9E3779B1)).astype(np.uint32)).astype(np.uint32) ^ seed32)
     cls2 = np.broadcast_to(cls[:, None], u.shape)
