@@ -33,7 +33,7 @@ SEED = 6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=125000, help="channels per GPU")
@@ -179,8 +179,11 @@ def run_b200(a):
     thr = P.synth_threshold_table(float(BP))
     rec = P.synth_recording(C, T, seed=SEED, BP_ms=float(BP), bursty=True, c0=rank * C, device=dev, thr=thr)
     cb = mua_b200.Codebook(S, np.array([SCLV]), device=dev)
-    want = ("cutoff", "end", "peak", "enc", "bits", "nsym")
+    # the timed path only needs the calibration window (64 samples/channel): cutoff, window end, peak, SCLV row;
+    # bit counts come out of the encoder itself
+    want = ("cutoff", "end", "peak", "enc")
     cal = P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=want)
+    max_end = H + T // 2
     slot = cb.worst_case_slot_bytes(T // 2 + 16)
     es = P.encode(rec, cb, cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0], slot_bytes=slot)
     dec = torch.zeros_like(rec.sym)
@@ -192,11 +195,11 @@ def run_b200(a):
         if ev: ev[1].record()
         P.encode(rec, cb, st, en, pk, ec, out=es)
         if ev: ev[2].record()
-        P.decode(es, rec, cb, st, en, pk, ec, out=dec)
+        P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=max_end)
         if ev: ev[3].record()
         rep = None
         if world > 1:
-            rep = D.gather_channel_report(es.total_bits, cal["nsym"][:, 0], ec, pk, C_total)
+            rep = D.gather_channel_report(es.total_bits, en - st, ec, pk, C_total)
         if ev: ev[4].record()
         return rep
 
@@ -232,15 +235,18 @@ def run_b200(a):
     mism = int(P.verify(rec, dec, S, st, en).item())
     assert mism == 0, "decode is not lossless: %d mismatches" % mism
     assert int(es.overflow.item()) == 0
-    assert torch.equal(es.total_bits, cal["bits"][:, 0]), "encoded length != SCLV . post histogram"
-    nsym_local = int(cal["nsym"][:, 0].sum().item())
+    # the reference's bit count (histogram of the post window . SCLV, get_BR_no_sort.py:287) from a separate full scan
+    ref = P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=("bits", "nsym"))
+    assert torch.equal(es.total_bits, ref["bits"][:, 0]), "encoded length != SCLV . post histogram"
+    assert torch.equal(ref["nsym"][:, 0], (en - st).to(torch.int64))
+    nsym_local = int(ref["nsym"][:, 0].sum().item())
     bits_local = int(es.total_bits.sum().item())
     tot = torch.tensor([nsym_local, bits_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
     nsym_all, bits_all = int(tot[0].item()), int(tot[1].item())
     if rep is None:
-        rep = D.gather_channel_report(es.total_bits, cal["nsym"][:, 0], cal["enc"][:, 0], cal["peak"][:, 0], C_total)
+        rep = D.gather_channel_report(es.total_bits, en - st, cal["enc"][:, 0], cal["peak"][:, 0], C_total)
     br = D.br_report(rep, BP) if rank == 0 else None
 
     ms_per_step = total_ms / a.steps
@@ -312,7 +318,8 @@ def run_e2e(a, rec, cb, dev, world, rank):
     h_stream = torch.empty((C, slot), dtype=torch.uint8, pin_memory=True)
     h_rep = torch.empty((C, 2), dtype=torch.int64, pin_memory=True)
     streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
-    want = ("cutoff", "end", "peak", "enc", "bits", "nsym")
+    want = ("cutoff", "end", "peak", "enc")
+    max_end = H + T // 2
     bufs = []
     maxb = max(bounds[i + 1] - bounds[i] for i in range(nblk))
     for s in streams:
@@ -337,9 +344,9 @@ def run_e2e(a, rec, cb, dev, world, rank):
                 P.calibrate(r, cb, [H], use_sort=True, window="truncate", want=want, out=cal)
                 st, en, pk, ec = cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0]
                 P.encode(r, cb, st, en, pk, ec, out=es)
-                P.decode(es, r, cb, st, en, pk, ec, out=dec)
+                P.decode(es, r, cb, st, en, pk, ec, out=dec, max_end=max_end)
                 repd[:n, 0] = es.total_bits[:n]
-                repd[:n, 1] = cal["nsym"][:n, 0]
+                repd[:n, 1] = (en - st)[:n]
                 h_stream[lo:hi].copy_(es.stream[:n], non_blocking=True)
                 h_rep[lo:hi].copy_(repd[:n], non_blocking=True)
         for s in streams:

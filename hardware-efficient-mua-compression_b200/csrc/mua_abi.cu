@@ -62,11 +62,18 @@ void layout_sizes(int S, int K, int Lmax, TabHdr* h) {
     h->S = S;
     h->K = K;
     h->Lmax = Lmax;
-    h->W = dec_window_bits(S, K, Lmax);
-    h->enc1_off = align_up((int)sizeof(TabHdr), 128);
-    h->enc2_off = align_up(h->enc1_off + S * K * 16 * 4, 128);
-    h->dec_off = align_up(h->enc2_off + S * K * 256 * 8, 128);
-    h->total_bytes = align_up(h->dec_off + ((S * K) << h->W) * 8, 128);
+    h->nsym = dec_nsym(S, K, Lmax);
+    h->W = h->nsym * Lmax;
+    h->enc1_off = align_up((int)sizeof(TabHdr), 512);
+    h->enc2_off = align_up(h->enc1_off + S * K * 16 * 4, 512);
+    int next = align_up(h->enc2_off + S * K * 256 * 8, 512);
+    h->enc4_off = 0;
+    if (Lmax <= 2) {
+        h->enc4_off = next;
+        next = align_up(next + S * K * 256 * 2, 512);
+    }
+    h->dec_off = next;
+    h->total_bytes = align_up(h->dec_off + ((S * K) << h->W) * 4, 512);
 }
 
 template <int S>
@@ -121,11 +128,13 @@ int mua_canonical_codebook(const uint8_t* h_lens, int K, int S, uint16_t* h_code
 
 size_t mua_tables_bytes(int S, int K) {
     if (S < 2 || S > MUA_MAX_S || K < 1 || K > MUA_MAX_K) return 0;
-    TabHdr h;
-    layout_sizes(S, K, 9, &h);   // worst-case window so the size does not depend on the rows
-    TabHdr h2;
-    layout_sizes(S, K, 1, &h2);
-    return (size_t)(h.total_bytes > h2.total_bytes ? h.total_bytes : h2.total_bytes);
+    int worst = 0;   // the size must not depend on the rows: take the maximum over Lmax
+    for (int L = 1; L <= 9; ++L) {
+        TabHdr h;
+        layout_sizes(S, K, L, &h);
+        if (h.total_bytes > worst) worst = h.total_bytes;
+    }
+    return (size_t)worst;
 }
 
 int mua_build_tables(void* d_tables, const uint8_t* h_lens, const uint16_t* h_codes, int S, int K, void* stream) {
@@ -300,19 +309,17 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     P.total_bits = d_total_bits; P.overflow = d_overflow;
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
     if (h.Lmax <= 2) {
-        constexpr int RW = 128;
-        const int smem = EncSmem<RW>::PER_WARP * ENC_WARPS;
-        cudaError_t e = cudaFuncSetAttribute(k_encode<RW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int smem = EncFastSmem::PER_WARP * ENC_WARPS;
+        cudaError_t e = cudaFuncSetAttribute(k_encode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");
         const int grid = ctas_needed < sm_count() * 4 ? ctas_needed : sm_count() * 4;
-        k_encode<RW, true><<<grid, ENC_WARPS * 32, smem, st>>>(P);
+        k_encode_fast<<<grid, ENC_WARPS * 32, smem, st>>>(P);
     } else {
-        constexpr int RW = 512;
-        const int smem = EncSmem<RW>::PER_WARP * ENC_WARPS;
-        cudaError_t e = cudaFuncSetAttribute(k_encode<RW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int smem = EncGenSmem::PER_WARP * ENC_WARPS;
+        cudaError_t e = cudaFuncSetAttribute(k_encode_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");
         const int grid = ctas_needed < sm_count() * 3 ? ctas_needed : sm_count() * 3;
-        k_encode<RW, false><<<grid, ENC_WARPS * 32, smem, st>>>(P);
+        k_encode_gen<<<grid, ENC_WARPS * 32, smem, st>>>(P);
     }
     CHECK_LAUNCH("k_encode");
     return MUA_OK;
@@ -320,7 +327,7 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
 
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off, int32_t chunk_stride, const int64_t* d_off,
                int64_t stride, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
-               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, uint8_t* d_dec, void* stream) {
+               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end, uint8_t* d_dec, void* stream) {
     REQUIRE(d_stream && d_chunk_off && d_start && d_end && d_peak && d_enc && d_tables && d_dec, "NULL argument");
     REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
     REQUIRE(aligned16(d_dec), "d_dec must be 16-byte aligned");
@@ -335,18 +342,27 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
     P.off = d_off; P.stride = stride; P.C = C; P.S = S; P.start = d_start; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
     P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax; P.dec = d_dec;
-    const long long items = (long long)C * chunk_stride;
-    const long long blocks_needed = (items + DEC_THREADS - 1) / DEC_THREADS;
-    const int lut_bytes = ((h.S * h.K) << h.W) * 8;
-    if (lut_bytes <= 64 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lut_bytes);
-        if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
-        const long long cap = (long long)sm_count() * 8;
-        k_decode<true><<<(int)(blocks_needed < cap ? blocks_needed : cap), DEC_THREADS, lut_bytes, st>>>(P);
-    } else {
-        const long long cap = (long long)sm_count() * 16;
-        k_decode<false><<<(int)(blocks_needed < cap ? blocks_needed : cap), DEC_THREADS, 0, st>>>(P);
-    }
+    REQUIRE(slot_bytes < (1ll << 32), "slot_bytes must be < 4 GiB");
+    // chunks per channel that can be non-empty: ceil(max_end / CHUNK) when the caller bounds the window end
+    P.item_chunks = chunk_stride;
+    if (max_end > 0 && (max_end + TILE - 1) / TILE < chunk_stride) P.item_chunks = (max_end + TILE - 1) / TILE;
+    const long long groups = ((long long)C * P.item_chunks + 31) / 32;
+    const long long blocks_needed = (groups + DEC_WARPS - 1) / DEC_WARPS;
+    const int lut_bytes = ((h.S * h.K) << h.W) * 4;
+    const bool smem_lut = lut_bytes <= 32 * 1024;
+    const int smem = DEC_WARPS * DEC_PER_WARP + (smem_lut ? lut_bytes : 0);
+    const long long cap = (long long)sm_count() * 4;
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+#define MUA_LAUNCH_DEC(NS, SL)                                                                                        \
+    do {                                                                                                              \
+        cudaError_t e = cudaFuncSetAttribute(k_decode<NS, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
+        if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");                                          \
+        k_decode<NS, SL><<<grid, DEC_WARPS * 32, smem, st>>>(P);                                                     \
+    } while (0)
+    if (h.nsym == 4) { if (smem_lut) MUA_LAUNCH_DEC(4, true); else MUA_LAUNCH_DEC(4, false); }
+    else if (h.nsym == 2) { if (smem_lut) MUA_LAUNCH_DEC(2, true); else MUA_LAUNCH_DEC(2, false); }
+    else { if (smem_lut) MUA_LAUNCH_DEC(1, true); else MUA_LAUNCH_DEC(1, false); }
+#undef MUA_LAUNCH_DEC
     CHECK_LAUNCH("k_decode");
     return MUA_OK;
 }

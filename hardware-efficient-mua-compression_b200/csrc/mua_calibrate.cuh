@@ -32,29 +32,38 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
     }
     uint32_t* enc1 = reinterpret_cast<uint32_t*>(blob + T->enc1_off) + (size_t)(p * K + k) * 16;
     uint2* enc2 = reinterpret_cast<uint2*>(blob + T->enc2_off) + (size_t)(p * K + k) * 256;
-    unsigned long long* dec = reinterpret_cast<unsigned long long*>(blob + T->dec_off) + ((size_t)(p * K + k) << W);
+    uint32_t* dec = reinterpret_cast<uint32_t*>(blob + T->dec_off) + ((size_t)(p * K + k) << W);
     if (tid < 16) enc1[tid] = ((uint32_t)s_len[s_rank[tid]] << 16) | s_code[s_rank[tid]];
     {
         int r0 = s_rank[tid & 15], r1 = s_rank[tid >> 4];
         uint32_t l1 = s_len[r1];
         enc2[tid] = make_uint2(((uint32_t)s_code[r0] << l1) | s_code[r1], (uint32_t)s_len[r0] + l1);
     }
+    if (T->enc4_off) {   // Lmax <= 2: four 2-bit symbols per entry
+        uint16_t* enc4 = reinterpret_cast<uint16_t*>(blob + T->enc4_off) + (size_t)(p * K + k) * 256;
+        uint32_t code = 0, len = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = s_rank[(tid >> (2 * i)) & 3];   // s_rank saturates values >= S
+            code = (code << s_len[r]) | s_code[r];
+            len += s_len[r];
+        }
+        enc4[tid] = (uint16_t)(code | (len << 8));
+    }
+    const int nsym = T->nsym;
     for (int v = tid; v < (1 << W); v += blockDim.x) {
-        unsigned long long e = 0;
-        int used = 0, n = 0;
-        while (n < DEC_MAX_SYM) {
-            int hit = -1;
+        uint32_t e = 0;
+        int used = 0;
+        for (int n = 0; n < nsym; ++n) {
+            int hit = 0;   // the rows are Kraft-complete and W = nsym*Lmax, so a codeword always matches
             for (int r = 0; r < S; ++r) {
                 int l = s_len[r];
                 if (used + l <= W && (uint32_t)((v >> (W - used - l)) & ((1 << l) - 1)) == s_code[r]) { hit = r; break; }
             }
-            if (hit < 0) break;
-            e |= (unsigned long long)s_idx[hit] << (8 * n);
+            e |= (uint32_t)s_idx[hit] << (8 * n);
             used += s_len[hit];
-            ++n;
         }
-        e |= (unsigned long long)(n | (used << 4)) << 56;
-        dec[v] = e;
+        dec[v] = e | ((uint32_t)used << 28);
     }
 }
 
@@ -108,8 +117,10 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
     }
     for (int i = lane; i < nB * S; i += 32) (&s_snap[warp][0][0])[i] = 0;
     __syncwarp();
+    // the post window is only scanned when a post-window output was asked for
+    const bool need_post = P.post_m != nullptr || P.bits != nullptr || P.nsym != nullptr;
     int scan_end = 0;
-    for (int i = 0; i < nB; ++i) scan_end = max(scan_end, s_bnd[warp][i]);
+    for (int i = 0; i < (need_post ? nB : nH); ++i) scan_end = max(scan_end, s_bnd[warp][i]);
 
     int acc[S];
 #pragma unroll
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
         // boundaries inside (t0, t0 + CAL_TILE]
         for (int bi = 0; bi < nB; ++bi) {
             const int b = s_bnd[warp][bi];
-            if (b > t0 && b <= t0 + CAL_TILE) {
+            if (b > t0 && b <= t0 + CAL_TILE && (need_post || bi < nH)) {
                 const int nvalid = min(max(b - p0, 0), 16);
                 uint32_t m[4];
 #pragma unroll

@@ -9,15 +9,19 @@ namespace mua {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int TILE = MUA_CHUNK;        // symbols per warp tile == decode chunk
-constexpr int DEC_MAX_SYM = 7;         // symbols per decode-LUT entry (bytes 0..6)
 
 // ---- device table block (built by k_build_tables) ------------------------------------------
 // enc1 : uint32 [S][K][16]    raw nibble b -> (len << 16 | code) of rank[p][min(b,S-1)]
-// enc2 : uint2  [S][K][256]   raw nibble pair (b0 | b1<<4), b0 first in time -> {code, len}
-// dec  : uint64 [S][K][1<<W]  W-bit window -> bytes 0..6 symbols, byte 7 = n | used_bits << 4
+// enc2 : uint2  [S][K][256]   raw nibble pair (b0 | b1<<4), b0 first in time -> {code, len}   (general encoder)
+// enc4 : uint16 [S][K][256]   four saturated 2-bit symbols (q0 | q1<<2 | q2<<4 | q3<<6), q0 first in time
+//                             -> code | len << 8; only when Lmax <= 2 (fast encoder), else absent
+// dec  : uint32 [S][K][1<<W]  W = nsym*Lmax bit window -> nsym symbols, one per byte (first symbol in
+//                             byte 0, values < 16) | used_bits << 28
 struct TabHdr {
     int32_t S, K, Lmax, W;
-    int32_t enc1_off, enc2_off, dec_off, total_bytes;
+    int32_t nsym;                    // symbols decoded per LUT lookup (4, 2 or 1)
+    int32_t enc1_off, enc2_off, enc4_off, dec_off, total_bytes;
+    int32_t pad[6];
     uint8_t lens[MUA_MAX_K][16];     // SCLV rows (Stored_SCLVs_S_<S>.pkl), ascending lengths
     uint16_t codes[MUA_MAX_K][16];   // codeword of rank r
     uint8_t rank[MUA_MAX_S][16];     // rank[p][s]: approx_sort permutation for peak p (functions_1.py:75-90)
@@ -26,10 +30,16 @@ struct TabHdr {
 
 __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-// decode window width: wide window while the whole LUT set stays small, else the minimum
-__host__ __device__ inline int dec_window_bits(int S, int K, int Lmax) {
-    if (S * K <= 6) return 10;
-    return Lmax > 8 ? Lmax : 8;
+// symbols per decode lookup (window W = nsym*Lmax bits): 4 when four lookups fit one 32-bit snapshot
+// (W <= 8), else 2 (W <= 12), else 1 -- and only while the LUT set of all (peak,row) pairs stays small
+__host__ __device__ inline int dec_nsym(int S, int K, int Lmax) {
+    const int ns[2] = {4, 2};
+    const int wmax[2] = {8, 12};
+    for (int i = 0; i < 2; ++i) {
+        const int W = ns[i] * Lmax;
+        if (W <= wmax[i] && (long long)S * K * (1ll << W) * 4 <= 32 * 1024) return ns[i];
+    }
+    return 1;
 }
 
 // Closed form of approx_sort's permutation (functions_1.py:75-90).

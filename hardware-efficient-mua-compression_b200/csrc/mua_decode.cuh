@@ -10,6 +10,7 @@ struct DecParams {
     int64_t slot_bytes;
     const uint32_t* chunk_off;
     int32_t chunk_stride;
+    int32_t item_chunks;        // chunks per channel that can be non-empty (<= chunk_stride)
     const int64_t* off;
     int64_t stride;
     int32_t C, S;
@@ -22,89 +23,155 @@ struct DecParams {
     uint8_t* dec;
 };
 
-constexpr int DEC_THREADS = 128;
+// One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks.
+//   * the lanes' stream bytes are staged into shared memory by the whole warp with coalesced 16-byte
+//     loads (272 B per lane and stage, byte-swapped to MSB-first words on the way in);
+//   * every LUT lookup decodes exactly NSYM symbols (window W = NSYM*Lmax bits), so output words are
+//     produced at fixed positions -- no variable-length output assembly;
+//   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
+//     writes out with coalesced 16-byte stores.
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_STR_W = 69;          // staged stream words per lane (68 used + 1 pad: odd stride, no bank conflicts)
+constexpr int DEC_STR_PIECES = 17;     // 16-byte pieces staged per lane: 272 B = 128 bits of alignment slack + 2048 bits
+constexpr int DEC_OUT_B = 144;         // output tile row: 128 B + 16 B pad
+constexpr int DEC_PER_WARP = 32 * DEC_STR_W * 4 + 32 * DEC_OUT_B;
 
-__device__ __forceinline__ void dec_store_bytes(uint8_t* dst, unsigned long long lo, unsigned long long hi, int from, int to) {
-    for (int k = from; k < to; ++k) dst[k] = (uint8_t)((k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8))) & 0xFF);
-}
-
-template <bool SMEM_LUT>
-__global__ void __launch_bounds__(DEC_THREADS) k_decode(const __grid_constant__ DecParams P) {
-    extern __shared__ __align__(16) unsigned long long s_lut[];
+template <int NSYM, bool SMEM_LUT>
+__global__ void __launch_bounds__(DEC_WARPS * 32, 3) k_decode(const __grid_constant__ DecParams P) {
+    extern __shared__ __align__(16) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
-    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax) return;   // host view does not match the table block
-    const unsigned long long* g_lut = reinterpret_cast<const unsigned long long*>(P.tab + T->dec_off);
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != NSYM) return;   // host view does not match the table block
+    const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DEC_PER_WARP);
+    uint8_t* s_out = dsm + warp * DEC_PER_WARP + 32 * DEC_STR_W * 4;
+    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DEC_WARPS * DEC_PER_WARP);
     if (SMEM_LUT) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DEC_WARPS * DEC_PER_WARP);
         const int nent = (T->S * K) << W;
-        for (int i = threadIdx.x; i < nent; i += blockDim.x) s_lut[i] = g_lut[i];
+        for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
         __syncthreads();
     }
-    const long long nitems = (long long)P.C * P.chunk_stride;
-    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
-         item += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(item / P.chunk_stride), j = (int)(item % P.chunk_stride);
-        const int start = P.start[c], end = P.end[c];
-        if (end <= start || start < 0) continue;
-        const int j0 = start / TILE;
-        const int nch = (end + TILE - 1) / TILE - j0;
-        if (j >= nch) continue;
-        const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
-        int rem = b - a;
-        const unsigned long long* lut = (SMEM_LUT ? s_lut : g_lut) + ((size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W);
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(P.stream + (size_t)c * P.slot_bytes);
-        const uint32_t nwords = (uint32_t)(P.slot_bytes >> 2);
-        const uint32_t bitpos = P.chunk_off[(size_t)c * P.chunk_stride + j];
-        uint32_t widx = bitpos >> 5;
-        const int sh = bitpos & 31;
-        auto ldw = [&](uint32_t i) -> uint32_t { return i < nwords ? bswap32(__ldg(sw + i)) : 0u; };
-        unsigned long long buf = ((unsigned long long)ldw(widx) << 32) | ldw(widx + 1);
-        widx += 2;
-        buf <<= sh;
-        int avail = 64 - sh;
+    const int periods_per_stage = 2048 / (128 * T->Lmax);        // 128-symbol periods one staged row is good for
+    const long long nitems = (long long)P.C * P.item_chunks;
+    const long long ngroups = (nitems + 31) / 32;
+    const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
 
-        const int64_t row = P.off ? P.off[c] : (int64_t)c * P.stride;
-        const int lead = a & 15;
-        uint8_t* dst = P.dec + row + (a - lead);   // 16-byte aligned
-        unsigned long long lo = 0, hi = 0, ex = 0;
-        int oc = lead;
-        bool first = lead > 0;
-        while (rem > 0) {
-            if (avail < 32) {
-                buf |= (unsigned long long)ldw(widx++) << (32 - avail);
-                avail += 32;
-            }
-            const unsigned long long e = lut[buf >> (64 - W)];
-            int nsy = (int)((e >> 56) & 15);
-            const int used = (int)(e >> 60);
-            unsigned long long syms = e & 0x00FFFFFFFFFFFFFFull;
-            if (nsy == 0) break;   // corrupt table/stream: never loops forever
-            if (nsy > rem) {
-                nsy = rem;
-                syms &= (1ull << (8 * nsy)) - 1ull;
-            }
-            buf <<= used;
-            avail -= used;
-            rem -= nsy;
-            if (oc < 8) {
-                lo |= syms << (8 * oc);
-                if (oc) hi |= syms >> (64 - 8 * oc);
-            } else {
-                const int o2 = oc - 8;
-                hi |= syms << (8 * o2);
-                if (o2) ex |= syms >> (64 - 8 * o2);
-            }
-            oc += nsy;
-            if (oc >= 16) {
-                if (!first) *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-                else dec_store_bytes(dst, lo, hi, lead, 16);
-                first = false;
-                dst += 16;
-                lo = ex; hi = 0; ex = 0;
-                oc -= 16;
+    for (long long g = (long long)blockIdx.x * DEC_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DEC_WARPS) {
+        // ---- this lane's chunk ----
+        const long long item = g * 32 + lane;
+        int rem = 0;
+        uint32_t bitpos = 0;
+        const uint8_t* sbase = P.stream;
+        uint8_t* optr = P.dec;
+        const uint32_t* lut = SMEM_LUT ? s_lut : g_lut;
+        if (item < nitems) {
+            const int c = (int)(item / P.item_chunks), j = (int)(item % P.item_chunks);
+            const int start = P.start[c], end = P.end[c];
+            if (end > start && start >= 0) {
+                const int j0 = start / TILE;
+                const int nch = (end + TILE - 1) / TILE - j0;
+                if (j < nch) {
+                    const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
+                    rem = b - a;
+                    bitpos = P.chunk_off[(size_t)c * P.chunk_stride + j];
+                    sbase = P.stream + (size_t)c * P.slot_bytes;
+                    optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
+                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W;
+                }
             }
         }
-        if (oc > 0) dec_store_bytes(dst, lo, hi, first ? lead : 0, oc);
+        int done = 0;                                            // symbols already written out
+        while (__any_sync(FULL, rem > 0)) {
+            // ---- stage 272 stream bytes per lane, starting at the 16-byte unit holding `bitpos` ----
+            const uint32_t cur_al = (bitpos >> 7) << 4;
+            const unsigned long long src_lane = reinterpret_cast<unsigned long long>(sbase) + cur_al;
+            __syncwarp();
+#pragma unroll 1
+            for (int i = 0; i < DEC_STR_PIECES; ++i) {
+                const int p = i * 32 + lane;
+                const int r = p / DEC_STR_PIECES, col = p - r * DEC_STR_PIECES;
+                const unsigned long long src = __shfl_sync(FULL, src_lane, r);
+                const uint32_t al_r = __shfl_sync(FULL, cur_al, r);
+                const int rem_r = __shfl_sync(FULL, rem, r);
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (rem_r > 0 && al_r + col * 16 + 16 <= slot_bytes) v = __ldg(reinterpret_cast<const uint4*>(src) + col);
+                uint32_t* d = s_str + r * DEC_STR_W + col * 4;
+                d[0] = bswap32(v.x); d[1] = bswap32(v.y); d[2] = bswap32(v.z); d[3] = bswap32(v.w);
+            }
+            __syncwarp();
+            const uint32_t* rowp = s_str + lane * DEC_STR_W;
+            const uint32_t boff = bitpos - cur_al * 8;           // 0..127
+            uint32_t rp = boff >> 5;
+            uint32_t hi = rowp[rp], lo = rowp[rp + 1];
+            rp += 2;
+            uint32_t off = boff & 31;
+            uint32_t consumed = 0;                               // bits consumed in this stage
+
+            for (int per = 0; per < periods_per_stage && __any_sync(FULL, rem > 0); ++per) {
+                // ---- 128 symbols per lane into the output tile ----
+                uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DEC_OUT_B);
+#pragma unroll 2
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t ow[4];
+                    if (NSYM == 4) {
+                        // one 32-bit snapshot feeds 4 lookups of <= 8 bits; refill check once per 16 symbols
+                        const uint32_t x = __funnelshift_l(lo, hi, off);
+                        uint32_t o = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t e = lut[(x << o) >> (32 - W)];
+                            ow[k] = e & 0x0F0F0F0Fu;
+                            o += e >> 28;
+                        }
+                        off += o;
+                        consumed += o;
+                        if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t wsym = 0;
+#pragma unroll
+                            for (int h = 0; h < 4 / NSYM; ++h) {
+                                const uint32_t x = __funnelshift_l(lo, hi, off);
+                                const uint32_t e = lut[x >> (32 - W)];
+                                wsym |= (e & 0x0F0F0F0Fu) << (8 * NSYM * h);
+                                const uint32_t used = e >> 28;
+                                off += used;
+                                consumed += used;
+                                if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
+                            }
+                            ow[k] = wsym;
+                        }
+                    }
+                    orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+                __syncwarp();
+                // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
+                const int vrow_self = min(max(rem, 0), 128);     // valid bytes of my row in this period
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3), col = lane & 7;
+                    const int vr = __shfl_sync(FULL, vrow_self, r);
+                    const unsigned long long dptr = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(optr) + done, r);
+                    if (col * 16 < vr) {
+                        const uint8_t* sp = s_out + r * DEC_OUT_B + col * 16;
+                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
+                        if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
+                            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
+                        } else {   // window edge or unaligned first chunk: byte stores
+                            const int nbyte = min(16, vr - col * 16);
+                            for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                        }
+                    }
+                }
+                __syncwarp();
+                if (rem > 0) { rem -= 128; done += 128; }
+            }
+            bitpos += consumed;
+            if (rem <= 0) rem = 0;
+        }
     }
 }
 

@@ -213,9 +213,11 @@ def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None,
     return out
 
 
-def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, enc, out: torch.Tensor = None):
+def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, enc, out: torch.Tensor = None,
+           max_end: int = 0):
     """Stage 6 (mua_decode): symbols written back at their absolute bin index into a buffer with the
-    layout of `rec.sym` (bytes outside the window are left as they were; a fresh buffer is zeroed)."""
+    layout of `rec.sym` (bytes outside the window are left as they were; a fresh buffer is zeroed).
+    max_end: host-known upper bound of `end` (0 = unknown); it only trims the launch."""
     lib = _lib.load()
     if out is None:
         out = torch.zeros_like(rec.sym)
@@ -226,7 +228,7 @@ def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, e
     with torch.cuda.device(rec.device):
         _lib.check(lib.mua_decode(_ptr(es.stream), es.slot_bytes, _ptr(es.chunk_off), es.chunk_stride, _ptr(rec.off),
                                   int(rec.stride), rec.C, cb.S, _ptr(start), _ptr(end), _ptr(peak), _ptr(enc),
-                                  _ptr(cb.d_tables), cb.K, cb.Lmax, _ptr(out), _stream()))
+                                  _ptr(cb.d_tables), cb.K, cb.Lmax, int(max_end), _ptr(out), _stream()))
     return out
 
 

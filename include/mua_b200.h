@@ -149,12 +149,14 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
 /* ---- stage 6: table-driven chunk-parallel decode ------------------------------------------ */
 
 /* Inverse of mua_encode: symbols are written back at their absolute bin index, i.e. d_dec uses the
- * same layout (d_off/stride) as the input; bytes outside [start,end) are not touched. */
+ * same layout (d_off/stride) as the input; bytes outside [start,end) are not touched.
+ * max_end: an upper bound of every d_end[c] known to the host (e.g. H + T/2), or 0 if unknown; it
+ * only sizes the launch (chunks past it are never scheduled). */
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off,
                int32_t chunk_stride, const int64_t* d_off, int64_t stride, int32_t C, int32_t S,
                const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
-               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, uint8_t* d_dec,
-               void* stream);
+               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end,
+               uint8_t* d_dec, void* stream);
 
 /* Round-trip check on the device: counts positions in [start,end) where d_dec != min(d_sym, S-1).
  * d_mismatch : uint64 [1] (zeroed by the call). */
