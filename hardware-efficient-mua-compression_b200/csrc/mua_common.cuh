@@ -102,6 +102,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
+// every byte -> 0xFF if its bit 7 is set, else 0x00 (PRMT sign-replicate mode; __byte_perm masks the
+// replicate bit of the selector away, so this needs the PTX form)
+__device__ __forceinline__ uint32_t byte_msb_mask(uint32_t v) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(FULL, v, d);

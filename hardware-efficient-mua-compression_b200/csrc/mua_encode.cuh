@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t lo7 = w[j] & 0x7F7F7F7Fu;
                     const uint32_t g = (lo7 + satk) | w[j];                  // bit 7 of a byte: value > S-1
-                    const uint32_t m = __byte_perm(g, 0, 0xba98);             // 0xFF where bit 7 is set
+                    const uint32_t m = byte_msb_mask(g);                      // 0xFF where bit 7 is set
                     const uint32_t ws = (w[j] & ~m) | (satv & m);             // min(byte, S-1): 2-bit symbols
                     const uint32_t a = (((ws * 0x01041040u) >> 23) & 0x1FEu) | lut4_off;
                     const uint32_t e = *reinterpret_cast<const uint16_t*>(smem_raw + a);
