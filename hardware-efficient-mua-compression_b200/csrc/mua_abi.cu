@@ -351,7 +351,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     const int lut_bytes = ((h.S * h.K) << h.W) * 4;
     const bool smem_lut = lut_bytes <= 32 * 1024;
     const int smem = DEC_WARPS * DEC_PER_WARP + (smem_lut ? lut_bytes : 0);
-    const long long cap = (long long)sm_count() * 4;
+    const long long cap = (long long)sm_count() * 6;
     const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
 #define MUA_LAUNCH_DEC(NS, SL)                                                                                        \
     do {                                                                                                              \

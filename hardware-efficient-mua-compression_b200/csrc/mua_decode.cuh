@@ -24,28 +24,53 @@ struct DecParams {
 };
 
 // One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks.
-//   * the lanes' stream bytes are staged into shared memory by the whole warp with coalesced 16-byte
-//     loads (272 B per lane and stage, byte-swapped to MSB-first words on the way in);
+//   * every lane streams its own chunk of the bitstream with 16-byte loads into a 4-word register
+//     queue, one load ahead of use (no staging buffer: shared memory only holds the output tile and
+//     the LUT, so ~40 warps stay resident per SM and hide the LUT latency);
 //   * every LUT lookup decodes exactly NSYM symbols (window W = NSYM*Lmax bits), so output words are
-//     produced at fixed positions -- no variable-length output assembly;
+//     produced at fixed positions -- no variable-length output assembly; with NSYM = 4 one 32-bit
+//     snapshot of the stream feeds 4 lookups and the refill test runs once per 16 symbols;
 //   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
 //     writes out with coalesced 16-byte stores.
-constexpr int DEC_WARPS = 4;
-constexpr int DEC_STR_W = 69;          // staged stream words per lane (68 used + 1 pad: odd stride, no bank conflicts)
-constexpr int DEC_STR_PIECES = 17;     // 16-byte pieces staged per lane: 272 B = 128 bits of alignment slack + 2048 bits
-constexpr int DEC_OUT_B = 144;         // output tile row: 128 B + 16 B pad
-constexpr int DEC_PER_WARP = 32 * DEC_STR_W * 4 + 32 * DEC_OUT_B;
+constexpr int DEC_WARPS = 8;
+constexpr int DEC_OUT_B = 144;         // output tile row: 128 B + 16 B pad (conflict-free 16-byte rows)
+constexpr int DEC_PER_WARP = 32 * DEC_OUT_B;
+
+struct DecStream {
+    const uint4* sp;       // next 16-byte unit to prefetch
+    int urem;              // units left in the slot from sp on
+    uint32_t q0, q1, q2, q3;   // current unit, MSB-first words, q0 next
+    uint4 pf;              // prefetched unit (raw)
+    int qn;                // words left in q
+    __device__ __forceinline__ uint4 fetch() {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (urem > 0) v = __ldg(sp);
+        ++sp;
+        --urem;
+        return v;
+    }
+    __device__ __forceinline__ uint32_t pop() {
+        if (qn == 0) {
+            q0 = bswap32(pf.x); q1 = bswap32(pf.y); q2 = bswap32(pf.z); q3 = bswap32(pf.w);
+            qn = 4;
+            pf = fetch();
+        }
+        const uint32_t x = q0;
+        q0 = q1; q1 = q2; q2 = q3;
+        --qn;
+        return x;
+    }
+};
 
 template <int NSYM, bool SMEM_LUT>
-__global__ void __launch_bounds__(DEC_WARPS * 32, 3) k_decode(const __grid_constant__ DecParams P) {
+__global__ void __launch_bounds__(DEC_WARPS * 32, 4) k_decode(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
     if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != NSYM) return;   // host view does not match the table block
     const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DEC_PER_WARP);
-    uint8_t* s_out = dsm + warp * DEC_PER_WARP + 32 * DEC_STR_W * 4;
+    uint8_t* s_out = dsm + warp * DEC_PER_WARP;
     const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DEC_WARPS * DEC_PER_WARP);
     if (SMEM_LUT) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DEC_WARPS * DEC_PER_WARP);
@@ -53,10 +78,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 3) k_decode(const __grid_const
         for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
         __syncthreads();
     }
-    const int periods_per_stage = 2048 / (128 * T->Lmax);        // 128-symbol periods one staged row is good for
     const long long nitems = (long long)P.C * P.item_chunks;
     const long long ngroups = (nitems + 31) / 32;
-    const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
+    const int slot_units = (int)(P.slot_bytes >> 4);
+    const int wsh = 32 - W;
 
     for (long long g = (long long)blockIdx.x * DEC_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DEC_WARPS) {
         // ---- this lane's chunk ----
@@ -82,95 +107,75 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 3) k_decode(const __grid_const
                 }
             }
         }
-        int done = 0;                                            // symbols already written out
-        while (__any_sync(FULL, rem > 0)) {
-            // ---- stage 272 stream bytes per lane, starting at the 16-byte unit holding `bitpos` ----
-            const uint32_t cur_al = (bitpos >> 7) << 4;
-            const unsigned long long src_lane = reinterpret_cast<unsigned long long>(sbase) + cur_al;
-            __syncwarp();
-#pragma unroll 1
-            for (int i = 0; i < DEC_STR_PIECES; ++i) {
-                const int p = i * 32 + lane;
-                const int r = p / DEC_STR_PIECES, col = p - r * DEC_STR_PIECES;
-                const unsigned long long src = __shfl_sync(FULL, src_lane, r);
-                const uint32_t al_r = __shfl_sync(FULL, cur_al, r);
-                const int rem_r = __shfl_sync(FULL, rem, r);
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (rem_r > 0 && al_r + col * 16 + 16 <= slot_bytes) v = __ldg(reinterpret_cast<const uint4*>(src) + col);
-                uint32_t* d = s_str + r * DEC_STR_W + col * 4;
-                d[0] = bswap32(v.x); d[1] = bswap32(v.y); d[2] = bswap32(v.z); d[3] = bswap32(v.w);
-            }
-            __syncwarp();
-            const uint32_t* rowp = s_str + lane * DEC_STR_W;
-            const uint32_t boff = bitpos - cur_al * 8;           // 0..127
-            uint32_t rp = boff >> 5;
-            uint32_t hi = rowp[rp], lo = rowp[rp + 1];
-            rp += 2;
-            uint32_t off = boff & 31;
-            uint32_t consumed = 0;                               // bits consumed in this stage
+        // ---- open the stream at `bitpos` ----
+        DecStream st;
+        st.sp = reinterpret_cast<const uint4*>(sbase) + (bitpos >> 7);
+        st.urem = rem > 0 ? slot_units - (int)(bitpos >> 7) : 0;
+        st.qn = 0;
+        st.q0 = st.q1 = st.q2 = st.q3 = 0;
+        st.pf = st.fetch();
+        for (uint32_t k = 0; k < ((bitpos >> 5) & 3u); ++k) (void)st.pop();
+        uint32_t hi = st.pop(), lo = st.pop();
+        uint32_t off = bitpos & 31;
 
-            for (int per = 0; per < periods_per_stage && __any_sync(FULL, rem > 0); ++per) {
-                // ---- 128 symbols per lane into the output tile ----
-                uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DEC_OUT_B);
+        while (__any_sync(FULL, rem > 0)) {
+            // ---- 128 symbols per lane into the output tile ----
+            uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DEC_OUT_B);
 #pragma unroll 2
-                for (int q = 0; q < 8; ++q) {
-                    uint32_t ow[4];
-                    if (NSYM == 4) {
-                        // one 32-bit snapshot feeds 4 lookups of <= 8 bits; refill check once per 16 symbols
-                        const uint32_t x = __funnelshift_l(lo, hi, off);
-                        uint32_t o = 0;
+            for (int q = 0; q < 8; ++q) {
+                uint32_t ow[4];
+                if (NSYM == 4) {
+                    // one 32-bit snapshot feeds 4 lookups of <= 8 bits; refill test once per 16 symbols
+                    const uint32_t x = __funnelshift_l(lo, hi, off);
+                    uint32_t o = 0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t e = lut[(x << o) >> (32 - W)];
-                            ow[k] = e & 0x0F0F0F0Fu;
-                            o += e >> 28;
-                        }
-                        off += o;
-                        consumed += o;
-                        if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            uint32_t wsym = 0;
-#pragma unroll
-                            for (int h = 0; h < 4 / NSYM; ++h) {
-                                const uint32_t x = __funnelshift_l(lo, hi, off);
-                                const uint32_t e = lut[x >> (32 - W)];
-                                wsym |= (e & 0x0F0F0F0Fu) << (8 * NSYM * h);
-                                const uint32_t used = e >> 28;
-                                off += used;
-                                consumed += used;
-                                if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
-                            }
-                            ow[k] = wsym;
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t e = lut[(x << o) >> wsh];
+                        ow[k] = e & 0x0F0F0F0Fu;
+                        o += e >> 28;
                     }
-                    orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                }
-                __syncwarp();
-                // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
-                const int vrow_self = min(max(rem, 0), 128);     // valid bytes of my row in this period
-#pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + (lane >> 3), col = lane & 7;
-                    const int vr = __shfl_sync(FULL, vrow_self, r);
-                    const unsigned long long dptr = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(optr) + done, r);
-                    if (col * 16 < vr) {
-                        const uint8_t* sp = s_out + r * DEC_OUT_B + col * 16;
-                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
-                        if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
-                            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
-                        } else {   // window edge or unaligned first chunk: byte stores
-                            const int nbyte = min(16, vr - col * 16);
-                            for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                    off += o;
+                    if (off >= 32) { hi = lo; lo = st.pop(); off -= 32; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t wsym = 0;
+#pragma unroll
+                        for (int h = 0; h < 4 / NSYM; ++h) {
+                            const uint32_t x = __funnelshift_l(lo, hi, off);
+                            const uint32_t e = lut[x >> wsh];
+                            wsym |= (e & 0x0F0F0F0Fu) << (8 * NSYM * h);
+                            off += e >> 28;
+                            if (off >= 32) { hi = lo; lo = st.pop(); off -= 32; }
                         }
+                        ow[k] = wsym;
                     }
                 }
-                __syncwarp();
-                if (rem > 0) { rem -= 128; done += 128; }
+                orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
-            bitpos += consumed;
-            if (rem <= 0) rem = 0;
+            __syncwarp();
+            // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
+            const int vrow_self = min(max(rem, 0), 128);         // valid bytes of my row in this period
+            const unsigned long long optr_self = reinterpret_cast<unsigned long long>(optr);
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + (lane >> 3), col = lane & 7;
+                const int vr = __shfl_sync(FULL, vrow_self, r);
+                const unsigned long long dptr = __shfl_sync(FULL, optr_self, r);
+                if (col * 16 < vr) {
+                    const uint8_t* sp = s_out + r * DEC_OUT_B + col * 16;
+                    uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
+                    if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
+                        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
+                    } else {   // window edge or unaligned first chunk: byte stores
+                        const int nbyte = min(16, vr - col * 16);
+                        for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                    }
+                }
+            }
+            __syncwarp();
+            rem -= 128;
+            optr += 128;
         }
     }
 }

@@ -101,40 +101,159 @@ __device__ __forceinline__ void flush_last(const uint32_t* s_ring, uint8_t* out,
 }
 
 // ---------------------------------------------------------------------------------------------
-// fast encoder (Lmax <= 2)
+// fast encoder (Lmax <= 2): 2048-symbol tiles, 64 symbols (two 32-symbol halves) per lane
 // ---------------------------------------------------------------------------------------------
+constexpr int ETILE = 2 * TILE;        // symbols per warp tile of the fast encoder (= 2 decode chunks)
+constexpr int EF_NST = 2;              // TMA stages per warp (2 KB each)
+
 struct EncFastSmem {
-    static constexpr int RW = 128;                              // staging ring words (>= 2048 bits/tile + slack)
-    static constexpr int IN = 0;                                // ENC_NST * TILE bytes
-    static constexpr int LUT4 = IN + ENC_NST * TILE;            // 256 * 2, 512-byte aligned
+    static constexpr int RW = 256;                              // staging ring words (4096 bits/tile + slack)
+    static constexpr int IN = 0;                                // EF_NST * ETILE bytes
+    static constexpr int LUT4 = IN + EF_NST * ETILE;            // 256 * 2, 512-byte aligned
     static constexpr int LUT1 = LUT4 + 512;                     // 16 * 4
     static constexpr int RING = LUT1 + 64;                      // RW * 4
-    static constexpr int BARS = RING + RW * 4;                  // ENC_NST * 8
-    static constexpr int PER_WARP = (BARS + ENC_NST * 8 + 511) / 512 * 512;
+    static constexpr int BARS = RING + RW * 4;                  // EF_NST * 8
+    static constexpr int PER_WARP = (BARS + EF_NST * 8 + 511) / 512 * 512;
 };
+
+// inclusive warp scan: shfl.up with its in-range predicate feeding a predicated add (2 instructions/step)
+__device__ __forceinline__ uint32_t warp_incl_scan_p(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n\t.reg .u32 t;\n\t.reg .pred p;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}"
+                     : "+r"(v)
+                     : "r"(d));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// 32 symbols (two uint4) -> code bits (right aligned) and bit count: SWAR saturate to S-1 (5 ops per 4
+// symbols), gather the four 2-bit symbols of a word into an 8-bit index with one multiply, one 16-bit
+// LUT read per word (code | len << 8), shift/or tree.
+__device__ __forceinline__ void encode32(const uint4 q0, const uint4 q1, uint32_t lut4_saddr, uint32_t satk, uint32_t satv,
+                                         unsigned long long& acc, uint32_t& nb) {
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    uint32_t qc[8], ql[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t lo7 = w[j] & 0x7F7F7F7Fu;
+        const uint32_t g = (lo7 + satk) | w[j];                  // bit 7 of a byte: value > S-1
+        const uint32_t m = byte_msb_mask(g);                      // 0xFF where bit 7 is set
+        const uint32_t ws = (w[j] & ~m) | (satv & m);             // min(byte, S-1): 2-bit symbols
+        const uint32_t e = lds_u16((((ws * 0x01041040u) >> 23) & 0x1FEu) | lut4_saddr);
+        qc[j] = e & 0xFFu;
+        ql[j] = e >> 8;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) { qc[j] = (qc[j] << ql[j + 1]) | qc[j + 1]; ql[j] += ql[j + 1]; }
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) { qc[j] = (qc[j] << ql[j + 2]) | qc[j + 2]; ql[j] += ql[j + 2]; }
+    nb = ql[0] + ql[4];                                           // 32..64 bits
+    acc = ((unsigned long long)qc[0] << ql[4]) | qc[4];
+}
+
+// One tile of the fast encoder.  FULLT: the whole tile lies inside the window (every lane emits >= 64 bits).
+template <bool FULLT, uint32_t RM>
+__device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4_saddr, const uint32_t* s_lut1, uint32_t satk,
+                                              uint32_t satv, int ts, int start, int end, int lane, uint32_t* s_ring,
+                                              uint32_t& Pbits, uint32_t& carry, uint32_t& a_lane) {
+    unsigned long long acc0, acc1;
+    uint32_t nb0, nb1;
+    encode32(*reinterpret_cast<const uint4*>(tile), *reinterpret_cast<const uint4*>(tile + 16), lut4_saddr, satk, satv, acc0, nb0);
+    encode32(*reinterpret_cast<const uint4*>(tile + 32), *reinterpret_cast<const uint4*>(tile + 48), lut4_saddr, satk, satv, acc1, nb1);
+    if (!FULLT) {
+        // head/tail tile: a half outside the window emits nothing; a half cut by the window boundary is
+        // recoded symbol by symbol (at most two such halves per channel)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p0 = ts + lane * 64 + h * 32;
+            const int vlo = max(start - p0, 0), vhi = min(end - p0, 32);
+            if (vlo > 0 || vhi < 32) {
+                unsigned long long acc = 0;
+                uint32_t nb = 0;
+                for (int i = vlo; i < vhi; ++i) {
+                    const uint32_t e1 = s_lut1[min((uint32_t)tile[h * 32 + i], 15u)];
+                    acc = (acc << (e1 >> 16)) | (e1 & 0xFFFFu);
+                    nb += e1 >> 16;
+                }
+                if (h == 0) { acc0 = acc; nb0 = nb; } else { acc1 = acc; nb1 = nb; }
+            }
+        }
+    }
+    // ---- bit offsets ----
+    const uint32_t nb = nb0 + nb1;
+    const uint32_t incl = warp_incl_scan_p(nb);
+    const uint32_t Pnew = Pbits + __shfl_sync(FULL, incl, 31);
+    const uint32_t a = Pbits + incl - nb;
+    a_lane = a;
+    const uint32_t Wi = a >> 5;
+    // ---- place the two halves back to back: A at bit a, B at bit a + nb0 ----
+    const uint32_t sh0 = a & 31;
+    if (!FULLT) { acc0 = nb0 ? acc0 << (64 - nb0) : 0ull; acc1 = nb1 ? acc1 << (64 - nb1) : 0ull; }
+    else { acc0 <<= (64 - nb0); acc1 <<= (64 - nb1); }
+    const uint32_t Ahi = (uint32_t)(acc0 >> 32), Alo = (uint32_t)acc0;
+    uint32_t A0 = Ahi >> sh0;
+    const uint32_t A1 = __funnelshift_r(Alo, Ahi, sh0);
+    const uint32_t A2 = __funnelshift_r(0u, Alo, sh0);
+    const uint32_t e0 = sh0 + nb0;
+    const uint32_t nf0 = e0 >> 5;                                 // complete words of A: 0..2 (FULLT: 1..2)
+    const uint32_t sh1 = e0 & 31;
+    const uint32_t Bhi = (uint32_t)(acc1 >> 32), Blo = (uint32_t)acc1;
+    uint32_t B0 = Bhi >> sh1;
+    const uint32_t B1 = __funnelshift_r(Blo, Bhi, sh1);
+    const uint32_t B2 = __funnelshift_r(0u, Blo, sh1);
+    const uint32_t e1 = sh1 + nb1;
+    const uint32_t nf1 = e1 >> 5;                                 // complete words of B: 0..2 (FULLT: 1..2)
+    if (FULLT) {
+        B0 |= sh1 ? (nf0 == 1 ? A1 : A2) : 0u;                    // A's trailing partial word shares B's first word
+        const uint32_t tl = (e1 & 31) ? (nf1 == 1 ? B1 : B2) : 0u;
+        uint32_t incoming = __shfl_up_sync(FULL, tl, 1);
+        if (lane == 0) incoming = carry;
+        carry = __shfl_sync(FULL, tl, 31);
+        A0 |= incoming;
+        s_ring[Wi & RM] = A0;
+        if (nf0 == 2) s_ring[(Wi + 1) & RM] = A1;
+        s_ring[(Wi + nf0) & RM] = B0;
+        if (nf1 == 2) s_ring[(Wi + nf0 + 1) & RM] = B1;
+    } else {
+        B0 |= sh1 ? (nf0 == 0 ? A0 : (nf0 == 1 ? A1 : A2)) : 0u;
+        const uint32_t tl = (e1 & 31) ? (nf1 == 0 ? B0 : (nf1 == 1 ? B1 : B2)) : 0u;
+        const uint32_t incoming = tails_segmented(tl, (nf0 + nf1) > 0, carry, lane);
+        if (nf0 >= 1) A0 |= incoming; else B0 |= incoming;        // the word at Wi
+        if (nf0 >= 1) s_ring[Wi & RM] = A0;
+        if (nf0 == 2) s_ring[(Wi + 1) & RM] = A1;
+        if (nf1 >= 1) s_ring[(Wi + nf0) & RM] = B0;
+        if (nf1 == 2) s_ring[(Wi + nf0 + 1) & RM] = B1;
+    }
+    Pbits = Pnew;
+}
 
 __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_constant__ EncParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = EncFastSmem;
     constexpr uint32_t RM = SM::RW - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t wbase = warp * SM::PER_WARP;                 // byte offset of this warp's block
-    uint8_t* sm = smem_raw + wbase;
+    uint8_t* sm = smem_raw + warp * SM::PER_WARP;
     uint8_t* s_in = sm + SM::IN;
-    const uint32_t lut4_off = wbase + SM::LUT4;                 // multiple of 512: OR-able with idx*2
+    const uint32_t lut4_saddr = smem_u32(sm + SM::LUT4);          // 512-byte aligned: OR-able with idx*2
     uint32_t* s_lut1 = reinterpret_cast<uint32_t*>(sm + SM::LUT1);
     uint32_t* s_ring = reinterpret_cast<uint32_t*>(sm + SM::RING);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm + SM::BARS);
 
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, S = T->S;
-    if (S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || T->enc4_off == 0) {
+    if (S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || T->enc4_off == 0 || (lut4_saddr & 511u)) {
         if (threadIdx.x == 0) *P.overflow = 2;   // launch configuration does not match the table block
         return;
     }
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < ENC_NST; ++i) mbar_init(&s_bar[i], 1);
+        for (int i = 0; i < EF_NST; ++i) mbar_init(&s_bar[i], 1);
         fence_barrier_init();
     }
     __syncwarp();
@@ -163,111 +282,52 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_
                 __syncwarp();
             }
             const uint8_t* row = P.L.sym + ch_off(P.L, c);
-            const int A0 = start & ~(TILE - 1);
-            const int nt = (end - A0 + TILE - 1) / TILE;
+            const int A0 = start & ~(ETILE - 1);
+            const int nt = (end - A0 + ETILE - 1) / ETILE;
             const int rd_end = (end + 15) & ~15;
-            uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride;
+            // chunk (1024-symbol) side info: tile t holds chunks 2t+dj and 2t+dj+1, numbered from start/1024
+            uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride + (A0 / TILE - start / TILE);
             uint8_t* out = P.stream + (size_t)c * P.slot_bytes;
             uint32_t carry = 0;
 
             if (lane == 0) {   // prologue: fill the ring
                 uint32_t s2 = slot;
-                const int npro = nt < ENC_NST ? nt : ENC_NST;
+                const int npro = nt < EF_NST ? nt : EF_NST;
                 for (int t = 0; t < npro; ++t) {
-                    const int ts = A0 + t * TILE;
-                    const uint32_t bytes = (uint32_t)min(TILE, rd_end - ts);
+                    const int ts = A0 + t * ETILE;
+                    const uint32_t bytes = (uint32_t)min(ETILE, rd_end - ts);
                     mbar_expect_tx(&s_bar[s2], bytes);
-                    tma_load_1d(s_in + s2 * TILE, row + ts, bytes, &s_bar[s2]);
-                    s2 = (s2 + 1) & (ENC_NST - 1);
+                    tma_load_1d(s_in + s2 * ETILE, row + ts, bytes, &s_bar[s2]);
+                    s2 = (s2 + 1) & (EF_NST - 1);
                 }
             }
 
             int ts = A0;
-            const uint8_t* nxt = row + A0 + ENC_NST * TILE;      // source of the refill for the current slot
-            for (int t = 0; t < nt; ++t, ts += TILE, nxt += TILE) {
+            for (int t = 0; t < nt; ++t, ts += ETILE) {
                 mbar_wait(&s_bar[slot], parity);
-                const uint8_t* tile = s_in + slot * TILE + lane * 32;
-                const uint4 q0 = *reinterpret_cast<const uint4*>(tile);
-                const uint4 q1 = *reinterpret_cast<const uint4*>(tile + 16);
-                const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                if (lane == 0) co[t] = Pbits;
-
-                // ---- 32 symbols -> (acc, nb): saturate, gather 4 crumbs, one LUT read per word ----
-                uint32_t qc[8], ql[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t lo7 = w[j] & 0x7F7F7F7Fu;
-                    const uint32_t g = (lo7 + satk) | w[j];                  // bit 7 of a byte: value > S-1
-                    const uint32_t m = byte_msb_mask(g);                      // 0xFF where bit 7 is set
-                    const uint32_t ws = (w[j] & ~m) | (satv & m);             // min(byte, S-1): 2-bit symbols
-                    const uint32_t a = (((ws * 0x01041040u) >> 23) & 0x1FEu) | lut4_off;
-                    const uint32_t e = *reinterpret_cast<const uint16_t*>(smem_raw + a);
-                    qc[j] = e & 0xFFu;
-                    ql[j] = e >> 8;
+                const uint8_t* tile = s_in + slot * ETILE + lane * 64;
+                const uint32_t Pold = Pbits;
+                uint32_t a_lane;
+                const bool full = (ts >= start) && (ts + ETILE <= end);       // warp-uniform
+                if (full) enc_fast_tile<true, RM>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
+                else enc_fast_tile<false, RM>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
+                // chunk offsets: lane 0 starts the tile's first chunk, lane 16 its second
+                if ((lane & 15) == 0) {
+                    const int cs = ts + (lane >> 4) * TILE;                   // absolute start of that chunk
+                    if (cs + TILE > start && cs < end) co[2 * t + (lane >> 4)] = a_lane;
                 }
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) { qc[j] = (qc[j] << ql[j + 1]) | qc[j + 1]; ql[j] += ql[j + 1]; }
-#pragma unroll
-                for (int j = 0; j < 8; j += 4) { qc[j] = (qc[j] << ql[j + 2]) | qc[j + 2]; ql[j] += ql[j + 2]; }
-                uint32_t nb = ql[0] + ql[4];                                  // 32..64 bits
-                unsigned long long acc = ((unsigned long long)qc[0] << ql[4]) | qc[4];
-
-                const bool full = (ts >= start) && (ts + TILE <= end);       // warp-uniform
-                if (!full) {
-                    // head/tail tile: lanes outside the window emit nothing; a lane cut by the window
-                    // boundary recodes its valid symbols one by one (at most two such lanes per channel)
-                    const int p0 = ts + lane * 32;
-                    const int vlo = max(start - p0, 0), vhi = min(end - p0, 32);
-                    if (vlo >= vhi) {
-                        nb = 0;
-                        acc = 0;
-                    } else if (vlo > 0 || vhi < 32) {
-                        nb = 0;
-                        acc = 0;
-                        for (int i = vlo; i < vhi; ++i) {
-                            const uint32_t e1 = s_lut1[min((uint32_t)tile[i], 15u)];
-                            acc = (acc << (e1 >> 16)) | (e1 & 0xFFFFu);
-                            nb += e1 >> 16;
-                        }
-                    }
-                }
-
-                // ---- bit offsets and placement ----
-                const uint32_t incl = warp_incl_scan(nb, lane);
-                const uint32_t Pnew = Pbits + __shfl_sync(FULL, incl, 31);
-                const uint32_t a = Pbits + incl - nb;
-                const uint32_t sh = a & 31, Wi = a >> 5;
-                acc = nb ? acc << (64 - nb) : 0ull;                           // left-align
-                const uint32_t Ahi = (uint32_t)(acc >> 32), Alo = (uint32_t)acc;
-                uint32_t w0 = Ahi >> sh;
-                const uint32_t w1 = __funnelshift_r(Alo, Ahi, sh);
-                const uint32_t w2 = __funnelshift_r(0u, Alo, sh);
-                const uint32_t e = sh + nb;
-                const uint32_t nfull = e >> 5;                                // complete words: 0..2
-                const uint32_t tl = (e & 31) ? (nfull == 0 ? w0 : (nfull == 1 ? w1 : w2)) : 0u;
-                uint32_t incoming;
-                if (full) {   // every lane completes a word: the partial word comes from the previous lane
-                    incoming = __shfl_up_sync(FULL, tl, 1);
-                    if (lane == 0) incoming = carry;
-                    carry = __shfl_sync(FULL, tl, 31);
-                } else {
-                    incoming = tails_segmented(tl, nfull > 0, carry, lane);
-                }
-                w0 |= incoming;
-                if (nfull >= 1) s_ring[Wi & RM] = w0;
-                if (nfull == 2) s_ring[(Wi + 1) & RM] = w1;
-
                 // ---- flush complete 128-bit units; refill the TMA slot ----
                 __syncwarp();
-                flush_units<RM>(s_ring, out, Pbits, Pnew, slot_units, P.overflow, lane);
-                Pbits = Pnew;
+                for (uint32_t b = Pold; (b >> 7) < (Pbits >> 7); b += 32 * 128)
+                    flush_units<RM>(s_ring, out, b, Pbits, slot_units, P.overflow, lane);
                 __syncwarp();
-                if (lane == 0 && t + ENC_NST < nt) {
-                    const uint32_t bytes = (uint32_t)min(TILE, rd_end - (ts + ENC_NST * TILE));
+                if (lane == 0 && t + EF_NST < nt) {
+                    const int ts2 = ts + EF_NST * ETILE;
+                    const uint32_t bytes = (uint32_t)min(ETILE, rd_end - ts2);
                     mbar_expect_tx(&s_bar[slot], bytes);
-                    tma_load_1d(s_in + slot * TILE, nxt, bytes, &s_bar[slot]);
+                    tma_load_1d(s_in + slot * ETILE, row + ts2, bytes, &s_bar[slot]);
                 }
-                slot = (slot + 1) & (ENC_NST - 1);
+                slot = (slot + 1) & (EF_NST - 1);
                 parity ^= (slot == 0);
             }
             flush_last<RM>(s_ring, out, Pbits, carry, slot_units, P.overflow, lane);
