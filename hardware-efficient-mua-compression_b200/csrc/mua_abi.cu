@@ -347,22 +347,39 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     P.item_chunks = chunk_stride;
     if (max_end > 0 && (max_end + TILE - 1) / TILE < chunk_stride) P.item_chunks = (max_end + TILE - 1) / TILE;
     const long long groups = ((long long)C * P.item_chunks + 31) / 32;
-    const long long blocks_needed = (groups + DEC_WARPS - 1) / DEC_WARPS;
     const int lut_bytes = ((h.S * h.K) << h.W) * 4;
     const bool smem_lut = lut_bytes <= 32 * 1024;
-    const int smem = DEC_WARPS * DEC_PER_WARP + (smem_lut ? lut_bytes : 0);
-    const long long cap = (long long)sm_count() * 6;
-    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
-#define MUA_LAUNCH_DEC(NS, SL)                                                                                        \
-    do {                                                                                                              \
-        cudaError_t e = cudaFuncSetAttribute(k_decode<NS, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
-        if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");                                          \
-        k_decode<NS, SL><<<grid, DEC_WARPS * 32, smem, st>>>(P);                                                     \
+    if (h.nsym == 4 && h.Lmax <= 2) {
+        REQUIRE((long long)C * (slot_bytes >> 4) < (1ll << 32), "stream buffer must be < 64 GiB");
+        const int smem = DF_WARPS * DF_PER_WARP + (smem_lut ? lut_bytes : 0);
+        const long long blocks_needed = (groups + DF_WARPS - 1) / DF_WARPS;
+        const long long cap = (long long)sm_count() * 4;
+        const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+        if (smem_lut) {
+            cudaError_t e = cudaFuncSetAttribute(k_decode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+            k_decode_fast<true><<<grid, DF_WARPS * 32, smem, st>>>(P);
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(k_decode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+            k_decode_fast<false><<<grid, DF_WARPS * 32, smem, st>>>(P);
+        }
+    } else {
+        const int smem = DG_WARPS * DG_PER_WARP + (smem_lut ? lut_bytes : 0);
+        const long long blocks_needed = (groups + DG_WARPS - 1) / DG_WARPS;
+        const long long cap = (long long)sm_count() * 4;
+        const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+#define MUA_LAUNCH_DEC(NS, SL)                                                                                            \
+    do {                                                                                                                  \
+        cudaError_t e = cudaFuncSetAttribute(k_decode_gen<NS, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
+        if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");                                              \
+        k_decode_gen<NS, SL><<<grid, DG_WARPS * 32, smem, st>>>(P);                                                      \
     } while (0)
-    if (h.nsym == 4) { if (smem_lut) MUA_LAUNCH_DEC(4, true); else MUA_LAUNCH_DEC(4, false); }
-    else if (h.nsym == 2) { if (smem_lut) MUA_LAUNCH_DEC(2, true); else MUA_LAUNCH_DEC(2, false); }
-    else { if (smem_lut) MUA_LAUNCH_DEC(1, true); else MUA_LAUNCH_DEC(1, false); }
+        if (h.nsym == 4) { if (smem_lut) MUA_LAUNCH_DEC(4, true); else MUA_LAUNCH_DEC(4, false); }
+        else if (h.nsym == 2) { if (smem_lut) MUA_LAUNCH_DEC(2, true); else MUA_LAUNCH_DEC(2, false); }
+        else { if (smem_lut) MUA_LAUNCH_DEC(1, true); else MUA_LAUNCH_DEC(1, false); }
 #undef MUA_LAUNCH_DEC
+    }
     CHECK_LAUNCH("k_decode");
     return MUA_OK;
 }

@@ -23,67 +23,43 @@ struct DecParams {
     uint8_t* dec;
 };
 
+// ---- general decoder (any codebook) ----
 // One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks.
-//   * every lane streams its own chunk of the bitstream with 16-byte loads into a 4-word register
-//     queue, one load ahead of use (no staging buffer: shared memory only holds the output tile and
-//     the LUT, so ~40 warps stay resident per SM and hide the LUT latency);
+//   * the lanes' stream bytes are staged into shared memory by the whole warp with coalesced 16-byte
+//     loads (272 B per lane and stage, byte-swapped to MSB-first words on the way in);
 //   * every LUT lookup decodes exactly NSYM symbols (window W = NSYM*Lmax bits), so output words are
-//     produced at fixed positions -- no variable-length output assembly; with NSYM = 4 one 32-bit
-//     snapshot of the stream feeds 4 lookups and the refill test runs once per 16 symbols;
+//     produced at fixed positions -- no variable-length output assembly;
 //   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
 //     writes out with coalesced 16-byte stores.
-constexpr int DEC_WARPS = 8;
-constexpr int DEC_OUT_B = 144;         // output tile row: 128 B + 16 B pad (conflict-free 16-byte rows)
-constexpr int DEC_PER_WARP = 32 * DEC_OUT_B;
-
-struct DecStream {
-    const uint4* sp;       // next 16-byte unit to prefetch
-    int urem;              // units left in the slot from sp on
-    uint32_t q0, q1, q2, q3;   // current unit, MSB-first words, q0 next
-    uint4 pf;              // prefetched unit (raw)
-    int qn;                // words left in q
-    __device__ __forceinline__ uint4 fetch() {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (urem > 0) v = __ldg(sp);
-        ++sp;
-        --urem;
-        return v;
-    }
-    __device__ __forceinline__ uint32_t pop() {
-        if (qn == 0) {
-            q0 = bswap32(pf.x); q1 = bswap32(pf.y); q2 = bswap32(pf.z); q3 = bswap32(pf.w);
-            qn = 4;
-            pf = fetch();
-        }
-        const uint32_t x = q0;
-        q0 = q1; q1 = q2; q2 = q3;
-        --qn;
-        return x;
-    }
-};
+constexpr int DG_WARPS = 4;
+constexpr int DG_STR_W = 69;          // staged stream words per lane (68 used + 1 pad: odd stride, no bank conflicts)
+constexpr int DG_STR_PIECES = 17;     // 16-byte pieces staged per lane: 272 B = 128 bits of alignment slack + 2048 bits
+constexpr int DG_OUT_B = 144;         // output tile row: 128 B + 16 B pad
+constexpr int DG_PER_WARP = 32 * DG_STR_W * 4 + 32 * DG_OUT_B;
 
 template <int NSYM, bool SMEM_LUT>
-__global__ void __launch_bounds__(DEC_WARPS * 32, 4) k_decode(const __grid_constant__ DecParams P) {
+__global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
     if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != NSYM) return;   // host view does not match the table block
     const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* s_out = dsm + warp * DEC_PER_WARP;
-    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DEC_WARPS * DEC_PER_WARP);
+    uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DG_PER_WARP);
+    uint8_t* s_out = dsm + warp * DG_PER_WARP + 32 * DG_STR_W * 4;
+    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DG_WARPS * DG_PER_WARP);
     if (SMEM_LUT) {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DEC_WARPS * DEC_PER_WARP);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DG_WARPS * DG_PER_WARP);
         const int nent = (T->S * K) << W;
         for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
         __syncthreads();
     }
+    const int periods_per_stage = 2048 / (128 * T->Lmax);        // 128-symbol periods one staged row is good for
     const long long nitems = (long long)P.C * P.item_chunks;
     const long long ngroups = (nitems + 31) / 32;
-    const int slot_units = (int)(P.slot_bytes >> 4);
-    const int wsh = 32 - W;
+    const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
 
-    for (long long g = (long long)blockIdx.x * DEC_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DEC_WARPS) {
+    for (long long g = (long long)blockIdx.x * DG_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DG_WARPS) {
         // ---- this lane's chunk ----
         const long long item = g * 32 + lane;
         int rem = 0;
@@ -107,50 +83,210 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4) k_decode(const __grid_const
                 }
             }
         }
-        // ---- open the stream at `bitpos` ----
-        DecStream st;
-        st.sp = reinterpret_cast<const uint4*>(sbase) + (bitpos >> 7);
-        st.urem = rem > 0 ? slot_units - (int)(bitpos >> 7) : 0;
-        st.qn = 0;
-        st.q0 = st.q1 = st.q2 = st.q3 = 0;
-        st.pf = st.fetch();
-        for (uint32_t k = 0; k < ((bitpos >> 5) & 3u); ++k) (void)st.pop();
-        uint32_t hi = st.pop(), lo = st.pop();
-        uint32_t off = bitpos & 31;
+        int done = 0;                                            // symbols already written out
+        while (__any_sync(FULL, rem > 0)) {
+            // ---- stage 272 stream bytes per lane, starting at the 16-byte unit holding `bitpos` ----
+            const uint32_t cur_al = (bitpos >> 7) << 4;
+            const unsigned long long src_lane = reinterpret_cast<unsigned long long>(sbase) + cur_al;
+            __syncwarp();
+#pragma unroll 1
+            for (int i = 0; i < DG_STR_PIECES; ++i) {
+                const int p = i * 32 + lane;
+                const int r = p / DG_STR_PIECES, col = p - r * DG_STR_PIECES;
+                const unsigned long long src = __shfl_sync(FULL, src_lane, r);
+                const uint32_t al_r = __shfl_sync(FULL, cur_al, r);
+                const int rem_r = __shfl_sync(FULL, rem, r);
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (rem_r > 0 && al_r + col * 16 + 16 <= slot_bytes) v = __ldg(reinterpret_cast<const uint4*>(src) + col);
+                uint32_t* d = s_str + r * DG_STR_W + col * 4;
+                d[0] = bswap32(v.x); d[1] = bswap32(v.y); d[2] = bswap32(v.z); d[3] = bswap32(v.w);
+            }
+            __syncwarp();
+            const uint32_t* rowp = s_str + lane * DG_STR_W;
+            const uint32_t boff = bitpos - cur_al * 8;           // 0..127
+            uint32_t rp = boff >> 5;
+            uint32_t hi = rowp[rp], lo = rowp[rp + 1];
+            rp += 2;
+            uint32_t off = boff & 31;
+            uint32_t consumed = 0;                               // bits consumed in this stage
+
+            for (int per = 0; per < periods_per_stage && __any_sync(FULL, rem > 0); ++per) {
+                // ---- 128 symbols per lane into the output tile ----
+                uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DG_OUT_B);
+#pragma unroll 2
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t ow[4];
+                    if (NSYM == 4) {
+                        // one 32-bit snapshot feeds 4 lookups of <= 8 bits; refill check once per 16 symbols
+                        const uint32_t x = __funnelshift_l(lo, hi, off);
+                        uint32_t o = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t e = lut[(x << o) >> (32 - W)];
+                            ow[k] = e & 0x0F0F0F0Fu;
+                            o += e >> 28;
+                        }
+                        off += o;
+                        consumed += o;
+                        if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t wsym = 0;
+#pragma unroll
+                            for (int h = 0; h < 4 / NSYM; ++h) {
+                                const uint32_t x = __funnelshift_l(lo, hi, off);
+                                const uint32_t e = lut[x >> (32 - W)];
+                                wsym |= (e & 0x0F0F0F0Fu) << (8 * NSYM * h);
+                                const uint32_t used = e >> 28;
+                                off += used;
+                                consumed += used;
+                                if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
+                            }
+                            ow[k] = wsym;
+                        }
+                    }
+                    orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+                __syncwarp();
+                // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
+                const int vrow_self = min(max(rem, 0), 128);     // valid bytes of my row in this period
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3), col = lane & 7;
+                    const int vr = __shfl_sync(FULL, vrow_self, r);
+                    const unsigned long long dptr = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(optr) + done, r);
+                    if (col * 16 < vr) {
+                        const uint8_t* sp = s_out + r * DG_OUT_B + col * 16;
+                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
+                        if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
+                            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
+                        } else {   // window edge or unaligned first chunk: byte stores
+                            const int nbyte = min(16, vr - col * 16);
+                            for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                        }
+                    }
+                }
+                __syncwarp();
+                if (rem > 0) { rem -= 128; done += 128; }
+            }
+            bitpos += consumed;
+            if (rem <= 0) rem = 0;
+        }
+    }
+}
+
+// ---- fast decoder (NSYM = 4: codebooks with Lmax <= 2) ----
+// One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks and works in periods of
+// 128 symbols per lane:
+//   * stream bytes reach shared memory through cooperative 16-byte loads (4 lanes per row).  The
+//     loads of period k+1 are issued at the top of period k into registers and stored at its end, so
+//     their latency hides behind a whole period of decoding.  A period consumes 128..256 bits, so the
+//     window [bp+128, bp+512) loaded for the next period always covers it (64 B per lane);
+//   * one 32-bit snapshot of the stream feeds 4 LUT lookups (<= 8 bits each, 4 symbols each, fixed
+//     output positions); the refill test runs once per 16 symbols and the refill word is read one
+//     snapshot ahead of use;
+//   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
+//     writes out with coalesced 16-byte stores.
+constexpr int DF_WARPS = 8;
+constexpr int DF_STR_W = 20;           // staged words per lane and period: 16 + 4 pad (rows stay 16-byte aligned)
+constexpr int DF_OUT_B = 144;          // output tile row: 128 B + 16 B pad
+constexpr int DF_PER_WARP = 32 * DF_STR_W * 4 + 32 * DF_OUT_B;
+
+template <bool SMEM_LUT>
+__global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_constant__ DecParams P) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
+    const int K = T->K, W = T->W;
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->Lmax > 2) return;   // host view does not match the table block
+    const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DF_PER_WARP);
+    uint8_t* s_out = dsm + warp * DF_PER_WARP + 32 * DF_STR_W * 4;
+    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
+    if (SMEM_LUT) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
+        const int nent = (T->S * K) << W;
+        for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
+        __syncthreads();
+    }
+    const long long nitems = (long long)P.C * P.item_chunks;
+    const long long ngroups = (nitems + 31) / 32;
+    const uint32_t slot_units = (uint32_t)(P.slot_bytes >> 4);
+    const uint32_t last_unit = (uint32_t)((long long)P.C * slot_units - 1);   // host guarantees < 2^32 units
+    const uint4* units = reinterpret_cast<const uint4*>(P.stream);
+    const int wsh = 32 - W;
+    const int prow = lane >> 2, pcol = lane & 3;                 // cooperative load: 4 lanes per row, 8 rows per pass
+
+    for (long long g = (long long)blockIdx.x * DF_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DF_WARPS) {
+        // ---- this lane's chunk ----
+        const long long item = g * 32 + lane;
+        int rem = 0;
+        uint32_t bp = 0;                                         // bit position in the channel's stream
+        uint32_t ubase = 0;                                      // first 16-byte unit of the channel's slot
+        uint8_t* optr = P.dec;
+        const uint32_t* lut = SMEM_LUT ? s_lut : g_lut;
+        if (item < nitems) {
+            const int c = (int)(item / P.item_chunks), j = (int)(item % P.item_chunks);
+            const int start = P.start[c], end = P.end[c];
+            if (end > start && start >= 0) {
+                const int j0 = start / TILE;
+                const int nch = (end + TILE - 1) / TILE - j0;
+                if (j < nch) {
+                    const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
+                    rem = b - a;
+                    bp = P.chunk_off[(size_t)c * P.chunk_stride + j];
+                    ubase = (uint32_t)c * slot_units;
+                    optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
+                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W;
+                }
+            }
+        }
+        // ---- stage the first period's window synchronously ----
+        uint32_t wunit = bp >> 7;                                // slot-relative unit where the staged window starts
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + prow;
+            const uint32_t gu = __shfl_sync(FULL, ubase + wunit, r) + pcol;
+            const uint4 v = __ldg(units + min(gu, last_unit));
+            *reinterpret_cast<uint4*>(s_str + r * DF_STR_W + pcol * 4) = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+        }
+        __syncwarp();
 
         while (__any_sync(FULL, rem > 0)) {
+            // ---- issue the next period's window loads (consumed at the end of this period) ----
+            const uint32_t nunit = (bp + 128) >> 7;
+            uint4 nx4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + prow;
+                const uint32_t gu = __shfl_sync(FULL, ubase + nunit, r) + pcol;
+                nx4[i] = __ldg(units + min(gu, last_unit));
+            }
             // ---- 128 symbols per lane into the output tile ----
-            uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DEC_OUT_B);
+            const uint32_t* rowp = s_str + lane * DF_STR_W;
+            const uint32_t boff = bp - (wunit << 7);             // 0..255
+            uint32_t rp = boff >> 5;
+            uint32_t hi = rowp[rp], lo = rowp[rp + 1], nx = rowp[rp + 2];
+            rp += 3;
+            uint32_t off = boff & 31;
+            uint32_t consumed = 0;
+            uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DF_OUT_B);
 #pragma unroll 2
             for (int q = 0; q < 8; ++q) {
                 uint32_t ow[4];
-                if (NSYM == 4) {
-                    // one 32-bit snapshot feeds 4 lookups of <= 8 bits; refill test once per 16 symbols
-                    const uint32_t x = __funnelshift_l(lo, hi, off);
-                    uint32_t o = 0;
+                const uint32_t x = __funnelshift_l(lo, hi, off);
+                uint32_t o = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t e = lut[(x << o) >> wsh];
-                        ow[k] = e & 0x0F0F0F0Fu;
-                        o += e >> 28;
-                    }
-                    off += o;
-                    if (off >= 32) { hi = lo; lo = st.pop(); off -= 32; }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        uint32_t wsym = 0;
-#pragma unroll
-                        for (int h = 0; h < 4 / NSYM; ++h) {
-                            const uint32_t x = __funnelshift_l(lo, hi, off);
-                            const uint32_t e = lut[x >> wsh];
-                            wsym |= (e & 0x0F0F0F0Fu) << (8 * NSYM * h);
-                            off += e >> 28;
-                            if (off >= 32) { hi = lo; lo = st.pop(); off -= 32; }
-                        }
-                        ow[k] = wsym;
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t e = lut[(x << o) >> wsh];
+                    ow[k] = e & 0x0F0F0F0Fu;
+                    o += e >> 28;
                 }
+                off += o;
+                consumed += o;
+                if (off >= 32) { hi = lo; lo = nx; nx = rowp[rp++]; off -= 32; }
                 orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
             __syncwarp();
@@ -163,7 +299,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4) k_decode(const __grid_const
                 const int vr = __shfl_sync(FULL, vrow_self, r);
                 const unsigned long long dptr = __shfl_sync(FULL, optr_self, r);
                 if (col * 16 < vr) {
-                    const uint8_t* sp = s_out + r * DEC_OUT_B + col * 16;
+                    const uint8_t* sp = s_out + r * DF_OUT_B + col * 16;
                     uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
                     if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
                         *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
@@ -173,7 +309,17 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4) k_decode(const __grid_const
                     }
                 }
             }
+            // ---- install the next period's window ----
             __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + prow;
+                *reinterpret_cast<uint4*>(s_str + r * DF_STR_W + pcol * 4) =
+                    make_uint4(bswap32(nx4[i].x), bswap32(nx4[i].y), bswap32(nx4[i].z), bswap32(nx4[i].w));
+            }
+            __syncwarp();
+            wunit = nunit;
+            bp += consumed;
             rem -= 128;
             optr += 128;
         }
