@@ -189,9 +189,11 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
 //   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
 //     writes out with coalesced 16-byte stores.
 constexpr int DF_WARPS = 8;
-constexpr int DF_STR_W = 20;           // staged words per lane and period: 16 + 4 pad (rows stay 16-byte aligned)
+constexpr int DF_STR_W = 17;           // staged words per lane and period: 16 + 1 pad (odd stride: conflict-free refills)
+constexpr int DF_STR_B = (32 * DF_STR_W * 4 + 15) / 16 * 16;
 constexpr int DF_OUT_B = 144;          // output tile row: 128 B + 16 B pad
-constexpr int DF_PER_WARP = 32 * DF_STR_W * 4 + 32 * DF_OUT_B;
+constexpr int DF_PER_WARP = DF_STR_B + 32 * DF_OUT_B;
+constexpr int DF_LUT_REP = 4;          // LUT replicas, bank-interleaved: lane l reads replica l & 3
 
 template <bool SMEM_LUT>
 __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_constant__ DecParams P) {
@@ -202,12 +204,15 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
     const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DF_PER_WARP);
-    uint8_t* s_out = dsm + warp * DF_PER_WARP + 32 * DF_STR_W * 4;
-    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
+    uint8_t* s_out = dsm + warp * DF_PER_WARP + DF_STR_B;
+    // LUT in shared memory, 4 bank-interleaved replicas (entry e of replica r at word 4e + r): the 8
+    // lanes that share a replica spread over 8 disjoint banks instead of all 32 lanes over 32
+    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DF_WARPS * DF_PER_WARP) + (SMEM_LUT ? (lane & (DF_LUT_REP - 1)) : 0);
+    constexpr int LSH = SMEM_LUT ? 2 : 0;                        // log2(replicas): index scale
     if (SMEM_LUT) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
         const int nent = (T->S * K) << W;
-        for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
+        for (int i = threadIdx.x; i < nent * DF_LUT_REP; i += blockDim.x) dst[i] = g_lut[i >> 2];
         __syncthreads();
     }
     const long long nitems = (long long)P.C * P.item_chunks;
@@ -238,10 +243,14 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
                     bp = P.chunk_off[(size_t)c * P.chunk_stride + j];
                     ubase = (uint32_t)c * slot_units;
                     optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
-                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W;
+                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << (W + LSH);
                 }
             }
         }
+        // are the 32 chunks one contiguous run of the output (same channel, consecutive full chunks)?
+        const unsigned long long optr0 = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(optr), 0);
+        const bool contig = __all_sync(FULL, rem == TILE && reinterpret_cast<unsigned long long>(optr) == optr0 + (unsigned long long)lane * TILE &&
+                                                 (optr0 & 15) == 0);
         // ---- stage the first period's window synchronously ----
         uint32_t wunit = bp >> 7;                                // slot-relative unit where the staged window starts
         __syncwarp();
@@ -250,7 +259,8 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
             const int r = i * 8 + prow;
             const uint32_t gu = __shfl_sync(FULL, ubase + wunit, r) + pcol;
             const uint4 v = __ldg(units + min(gu, last_unit));
-            *reinterpret_cast<uint4*>(s_str + r * DF_STR_W + pcol * 4) = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+            uint32_t* d = s_str + r * DF_STR_W + pcol * 4;
+            d[0] = bswap32(v.x); d[1] = bswap32(v.y); d[2] = bswap32(v.z); d[3] = bswap32(v.w);
         }
         __syncwarp();
 
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
                 uint32_t o = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t e = lut[(x << o) >> wsh];
+                    const uint32_t e = lut[((x << o) >> wsh) << LSH];
                     ow[k] = e & 0x0F0F0F0Fu;
                     o += e >> 28;
                 }
@@ -291,21 +301,31 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
             }
             __syncwarp();
             // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
-            const int vrow_self = min(max(rem, 0), 128);         // valid bytes of my row in this period
-            const unsigned long long optr_self = reinterpret_cast<unsigned long long>(optr);
+            if (contig) {   // 32 full chunks back to back: row r lives at optr0 + r*1024, no shuffles needed
+                uint8_t* base = reinterpret_cast<uint8_t*>(optr0) + (TILE - rem) + (lane & 7) * 16;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3);
+                    *reinterpret_cast<uint4*>(base + (size_t)r * TILE) =
+                        *reinterpret_cast<const uint4*>(s_out + r * DF_OUT_B + (lane & 7) * 16);
+                }
+            } else {
+                const int vrow_self = min(max(rem, 0), 128);     // valid bytes of my row in this period
+                const unsigned long long optr_self = reinterpret_cast<unsigned long long>(optr);
 #pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-                const int r = i * 4 + (lane >> 3), col = lane & 7;
-                const int vr = __shfl_sync(FULL, vrow_self, r);
-                const unsigned long long dptr = __shfl_sync(FULL, optr_self, r);
-                if (col * 16 < vr) {
-                    const uint8_t* sp = s_out + r * DF_OUT_B + col * 16;
-                    uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
-                    if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
-                        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
-                    } else {   // window edge or unaligned first chunk: byte stores
-                        const int nbyte = min(16, vr - col * 16);
-                        for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3), col = lane & 7;
+                    const int vr = __shfl_sync(FULL, vrow_self, r);
+                    const unsigned long long dptr = __shfl_sync(FULL, optr_self, r);
+                    if (col * 16 < vr) {
+                        const uint8_t* sp = s_out + r * DF_OUT_B + col * 16;
+                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
+                        if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
+                            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
+                        } else {   // window edge or unaligned first chunk: byte stores
+                            const int nbyte = min(16, vr - col * 16);
+                            for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                        }
                     }
                 }
             }
@@ -314,8 +334,8 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = i * 8 + prow;
-                *reinterpret_cast<uint4*>(s_str + r * DF_STR_W + pcol * 4) =
-                    make_uint4(bswap32(nx4[i].x), bswap32(nx4[i].y), bswap32(nx4[i].z), bswap32(nx4[i].w));
+                uint32_t* d = s_str + r * DF_STR_W + pcol * 4;
+                d[0] = bswap32(nx4[i].x); d[1] = bswap32(nx4[i].y); d[2] = bswap32(nx4[i].z); d[3] = bswap32(nx4[i].w);
             }
             __syncwarp();
             wunit = nunit;

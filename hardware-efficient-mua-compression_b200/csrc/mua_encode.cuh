@@ -132,15 +132,15 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
     return v;
 }
 
-// 32 symbols (two uint4) -> code bits (right aligned) and bit count: SWAR saturate to S-1 (5 ops per 4
-// symbols), gather the four 2-bit symbols of a word into an 8-bit index with one multiply, one 16-bit
-// LUT read per word (code | len << 8), shift/or tree.
-__device__ __forceinline__ void encode32(const uint4 q0, const uint4 q1, uint32_t lut4_saddr, uint32_t satk, uint32_t satv,
-                                         unsigned long long& acc, uint32_t& nb) {
-    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    uint32_t qc[8], ql[8];
+// 16 symbols (one uint4) -> code bits (right aligned, <= 32) and bit count (16..32): SWAR saturate to
+// S-1 (5 ops per 4 symbols), gather the four 2-bit symbols of a word into an 8-bit index with one
+// multiply, one 16-bit LUT read per word (code | len << 8), shift/or tree.
+__device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uint32_t satk, uint32_t satv, uint32_t& code,
+                                         uint32_t& len) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t qc[4], ql[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
         const uint32_t lo7 = w[j] & 0x7F7F7F7Fu;
         const uint32_t g = (lo7 + satk) | w[j];                  // bit 7 of a byte: value > S-1
         const uint32_t m = byte_msb_mask(g);                      // 0xFF where bit 7 is set
@@ -149,12 +149,10 @@ __device__ __forceinline__ void encode32(const uint4 q0, const uint4 q1, uint32_
         qc[j] = e & 0xFFu;
         ql[j] = e >> 8;
     }
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) { qc[j] = (qc[j] << ql[j + 1]) | qc[j + 1]; ql[j] += ql[j + 1]; }
-#pragma unroll
-    for (int j = 0; j < 8; j += 4) { qc[j] = (qc[j] << ql[j + 2]) | qc[j + 2]; ql[j] += ql[j + 2]; }
-    nb = ql[0] + ql[4];                                           // 32..64 bits
-    acc = ((unsigned long long)qc[0] << ql[4]) | qc[4];
+    qc[0] = (qc[0] << ql[1]) | qc[1]; ql[0] += ql[1];
+    qc[2] = (qc[2] << ql[3]) | qc[3]; ql[2] += ql[3];
+    code = (qc[0] << ql[2]) | qc[2];
+    len = ql[0] + ql[2];
 }
 
 // One tile of the fast encoder.  FULLT: the whole tile lies inside the window (every lane emits >= 64 bits).
@@ -162,10 +160,25 @@ template <bool FULLT, uint32_t RM>
 __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4_saddr, const uint32_t* s_lut1, uint32_t satk,
                                               uint32_t satv, int ts, int start, int end, int lane, uint32_t* s_ring,
                                               uint32_t& Pbits, uint32_t& carry, uint32_t& a_lane) {
-    unsigned long long acc0, acc1;
-    uint32_t nb0, nb1;
-    encode32(*reinterpret_cast<const uint4*>(tile), *reinterpret_cast<const uint4*>(tile + 16), lut4_saddr, satk, satv, acc0, nb0);
-    encode32(*reinterpret_cast<const uint4*>(tile + 32), *reinterpret_cast<const uint4*>(tile + 48), lut4_saddr, satk, satv, acc1, nb1);
+    // The lane's 64 bytes are four 16-byte pieces.  With a 64-byte lane stride, reading piece k in
+    // every lane would be a 4-way bank conflict; lane l reads piece (k + rot) & 3, rot = (l >> 1) & 3,
+    // which is conflict-free, and a two-level select network puts the four results back in order.
+    const uint32_t rot = (lane >> 1) & 3;
+    uint32_t pc[4], pl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        encode16(*reinterpret_cast<const uint4*>(tile + 16 * ((k + rot) & 3)), lut4_saddr, satk, satv, pc[k], pl[k]);
+    {
+        const bool r1 = rot & 1, r2 = rot & 2;
+        uint32_t tc[4], tl4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tc[j] = r1 ? pc[(j + 3) & 3] : pc[j]; tl4[j] = r1 ? pl[(j + 3) & 3] : pl[j]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { pc[j] = r2 ? tc[(j + 2) & 3] : tc[j]; pl[j] = r2 ? tl4[(j + 2) & 3] : tl4[j]; }
+    }
+    unsigned long long acc0 = ((unsigned long long)pc[0] << pl[1]) | pc[1];
+    unsigned long long acc1 = ((unsigned long long)pc[2] << pl[3]) | pc[3];
+    uint32_t nb0 = pl[0] + pl[1], nb1 = pl[2] + pl[3];           // 32..64 bits each
     if (!FULLT) {
         // head/tail tile: a half outside the window emits nothing; a half cut by the window boundary is
         // recoded symbol by symbol (at most two such halves per channel)
