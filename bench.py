@@ -129,14 +129,14 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             out = self.p.communicate(timeout=5)[0]
@@ -155,8 +155,16 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        # keep the samples taken under load (upper half of the power readings): the sampler also sees the
+        # few idle milliseconds before the first and after the last step
+        if pw:
+            thr = 0.5 * (max(pw) + min(pw))
+            load = [s_ for s_, p_ in zip(sm, pw) if p_ >= thr] or sm
+        else:
+            load = sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_under_load": len(load),
+                "window": "warm-up + timed steps (same load)", "reasons": sorted(reasons)}
 
 
 def run_b200(a):
@@ -203,14 +211,18 @@ def run_b200(a):
         if ev: ev[4].record()
         return rep
 
-    for _ in range(max(a.warmup, 3)):
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_w = time.perf_counter()
+    nw = 0
+    while nw < max(a.warmup, 3) or (time.perf_counter() - t_w < 0.25 and nw < 200):   # >= 3 warm-up steps, >= 0.25 s under load
         step()
+        nw += 1
+        if nw % 8 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(a.steps)]
     t_end = torch.cuda.Event(enable_timing=True)
     rep = None
@@ -289,7 +301,7 @@ def run_b200(a):
     cpu = cpu_baseline_single(T) if rank == 0 else None
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": nw,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "channels_per_gpu": C, "bins": T, "total_channels": C_total,
