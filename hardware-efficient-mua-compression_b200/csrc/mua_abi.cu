@@ -351,10 +351,10 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     const bool smem_lut = lut_bytes <= 32 * 1024;
     if (h.nsym == 4 && h.Lmax <= 2) {
         REQUIRE((long long)C * (slot_bytes >> 4) < (1ll << 32), "stream buffer must be < 64 GiB");
-        const bool fast_smem_lut = lut_bytes * DF_LUT_REP <= 32 * 1024;
-        const int smem = DF_WARPS * DF_PER_WARP + (fast_smem_lut ? lut_bytes * DF_LUT_REP : 0);
+        const bool fast_smem_lut = smem_lut;
+        const int smem = DF_WARPS * DF_PER_WARP + (fast_smem_lut ? lut_bytes : 0);
         const long long blocks_needed = (groups + DF_WARPS - 1) / DF_WARPS;
-        const long long cap = (long long)sm_count() * 4;
+        const long long cap = (long long)sm_count() * 5;
         const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
         if (fast_smem_lut) {
             cudaError_t e = cudaFuncSetAttribute(k_decode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

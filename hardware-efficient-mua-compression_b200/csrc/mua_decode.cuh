@@ -178,25 +178,27 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
 
 // ---- fast decoder (NSYM = 4: codebooks with Lmax <= 2) ----
 // One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks and works in periods of
-// 128 symbols per lane:
-//   * stream bytes reach shared memory through cooperative 16-byte loads (4 lanes per row).  The
-//     loads of period k+1 are issued at the top of period k into registers and stored at its end, so
-//     their latency hides behind a whole period of decoding.  A period consumes 128..256 bits, so the
-//     window [bp+128, bp+512) loaded for the next period always covers it (64 B per lane);
+// DF_PER = 64 symbols per lane (small periods keep the shared-memory footprint per lane at ~130 B, so
+// ~40 warps stay resident per SM and hide the LUT latency of the serial per-lane decode chain):
+//   * stream bytes reach shared memory through cooperative 16-byte loads.  The loads of period k+1 are
+//     issued at the top of period k into registers and stored at its end, so their latency hides
+//     behind a whole period of decoding.  A period consumes 64..128 bits, so the 48-byte window that
+//     starts at the 16-byte unit holding bit bp+64 always covers the next period;
 //   * one 32-bit snapshot of the stream feeds 4 LUT lookups (<= 8 bits each, 4 symbols each, fixed
 //     output positions); the refill test runs once per 16 symbols and the refill word is read one
 //     snapshot ahead of use;
-//   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
-//     writes out with coalesced 16-byte stores.
+//   * decoded symbols go to a padded shared-memory tile (64 B per lane and period) that the warp
+//     writes out with coalesced 16-byte stores (4 lanes per row).
 constexpr int DF_WARPS = 8;
-constexpr int DF_STR_W = 17;           // staged words per lane and period: 16 + 1 pad (odd stride: conflict-free refills)
+constexpr int DF_PER = 64;             // symbols per lane and period
+constexpr int DF_NP = 3;               // 16-byte pieces staged per lane and period
+constexpr int DF_STR_W = 13;           // staged words per lane: 12 + 1 pad (odd stride: conflict-free refills)
 constexpr int DF_STR_B = (32 * DF_STR_W * 4 + 15) / 16 * 16;
-constexpr int DF_OUT_B = 144;          // output tile row: 128 B + 16 B pad
+constexpr int DF_OUT_B = 80;           // output tile row: 64 B + 16 B pad
 constexpr int DF_PER_WARP = DF_STR_B + 32 * DF_OUT_B;
-constexpr int DF_LUT_REP = 4;          // LUT replicas, bank-interleaved: lane l reads replica l & 3
 
 template <bool SMEM_LUT>
-__global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_constant__ DecParams P) {
+__global__ void __launch_bounds__(DF_WARPS * 32, 5) k_decode_fast(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
@@ -205,14 +207,11 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DF_PER_WARP);
     uint8_t* s_out = dsm + warp * DF_PER_WARP + DF_STR_B;
-    // LUT in shared memory, 4 bank-interleaved replicas (entry e of replica r at word 4e + r): the 8
-    // lanes that share a replica spread over 8 disjoint banks instead of all 32 lanes over 32
-    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DF_WARPS * DF_PER_WARP) + (SMEM_LUT ? (lane & (DF_LUT_REP - 1)) : 0);
-    constexpr int LSH = SMEM_LUT ? 2 : 0;                        // log2(replicas): index scale
+    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
     if (SMEM_LUT) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
         const int nent = (T->S * K) << W;
-        for (int i = threadIdx.x; i < nent * DF_LUT_REP; i += blockDim.x) dst[i] = g_lut[i >> 2];
+        for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
         __syncthreads();
     }
     const long long nitems = (long long)P.C * P.item_chunks;
@@ -221,7 +220,12 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
     const uint32_t last_unit = (uint32_t)((long long)P.C * slot_units - 1);   // host guarantees < 2^32 units
     const uint4* units = reinterpret_cast<const uint4*>(P.stream);
     const int wsh = 32 - W;
-    const int prow = lane >> 2, pcol = lane & 3;                 // cooperative load: 4 lanes per row, 8 rows per pass
+    // cooperative window load: piece p = i*32 + lane of 96 -> row p/3, column p%3
+    int prow[DF_NP], pcol[DF_NP];
+#pragma unroll
+    for (int i = 0; i < DF_NP; ++i) { const int p = i * 32 + lane; prow[i] = p / DF_NP; pcol[i] = p - prow[i] * DF_NP; }
+    // write-out: 4 lanes per 64-byte row; the two rows of a quarter-warp are 4 apart (conflict-free)
+    const int wrow = (lane >> 3) + 4 * ((lane >> 2) & 1), wcol = lane & 3;
 
     for (long long g = (long long)blockIdx.x * DF_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DF_WARPS) {
         // ---- this lane's chunk ----
@@ -243,54 +247,48 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
                     bp = P.chunk_off[(size_t)c * P.chunk_stride + j];
                     ubase = (uint32_t)c * slot_units;
                     optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
-                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << (W + LSH);
+                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W;
                 }
             }
         }
-        // are the 32 chunks one contiguous run of the output (same channel, consecutive full chunks)?
-        const unsigned long long optr0 = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(optr), 0);
-        const bool contig = __all_sync(FULL, rem == TILE && reinterpret_cast<unsigned long long>(optr) == optr0 + (unsigned long long)lane * TILE &&
-                                                 (optr0 & 15) == 0);
         // ---- stage the first period's window synchronously ----
         uint32_t wunit = bp >> 7;                                // slot-relative unit where the staged window starts
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + prow;
-            const uint32_t gu = __shfl_sync(FULL, ubase + wunit, r) + pcol;
+        for (int i = 0; i < DF_NP; ++i) {
+            const uint32_t gu = __shfl_sync(FULL, ubase + wunit, prow[i]) + pcol[i];
             const uint4 v = __ldg(units + min(gu, last_unit));
-            uint32_t* d = s_str + r * DF_STR_W + pcol * 4;
+            uint32_t* d = s_str + prow[i] * DF_STR_W + pcol[i] * 4;
             d[0] = bswap32(v.x); d[1] = bswap32(v.y); d[2] = bswap32(v.z); d[3] = bswap32(v.w);
         }
         __syncwarp();
 
         while (__any_sync(FULL, rem > 0)) {
             // ---- issue the next period's window loads (consumed at the end of this period) ----
-            const uint32_t nunit = (bp + 128) >> 7;
-            uint4 nx4[4];
+            const uint32_t nunit = (bp + DF_PER) >> 7;
+            uint4 nx4[DF_NP];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = i * 8 + prow;
-                const uint32_t gu = __shfl_sync(FULL, ubase + nunit, r) + pcol;
+            for (int i = 0; i < DF_NP; ++i) {
+                const uint32_t gu = __shfl_sync(FULL, ubase + nunit, prow[i]) + pcol[i];
                 nx4[i] = __ldg(units + min(gu, last_unit));
             }
-            // ---- 128 symbols per lane into the output tile ----
+            // ---- DF_PER symbols per lane into the output tile ----
             const uint32_t* rowp = s_str + lane * DF_STR_W;
-            const uint32_t boff = bp - (wunit << 7);             // 0..255
+            const uint32_t boff = bp - (wunit << 7);             // 0..191
             uint32_t rp = boff >> 5;
             uint32_t hi = rowp[rp], lo = rowp[rp + 1], nx = rowp[rp + 2];
             rp += 3;
             uint32_t off = boff & 31;
             uint32_t consumed = 0;
             uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DF_OUT_B);
-#pragma unroll 2
-            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+            for (int q = 0; q < DF_PER / 16; ++q) {
                 uint32_t ow[4];
                 const uint32_t x = __funnelshift_l(lo, hi, off);
                 uint32_t o = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t e = lut[((x << o) >> wsh) << LSH];
+                    const uint32_t e = lut[(x << o) >> wsh];
                     ow[k] = e & 0x0F0F0F0Fu;
                     o += e >> 28;
                 }
@@ -300,48 +298,39 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
                 orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
             __syncwarp();
-            // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
-            if (contig) {   // 32 full chunks back to back: row r lives at optr0 + r*1024, no shuffles needed
-                uint8_t* base = reinterpret_cast<uint8_t*>(optr0) + (TILE - rem) + (lane & 7) * 16;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + (lane >> 3);
-                    *reinterpret_cast<uint4*>(base + (size_t)r * TILE) =
-                        *reinterpret_cast<const uint4*>(s_out + r * DF_OUT_B + (lane & 7) * 16);
-                }
-            } else {
-                const int vrow_self = min(max(rem, 0), 128);     // valid bytes of my row in this period
-                const unsigned long long optr_self = reinterpret_cast<unsigned long long>(optr);
+            {
+            // ---- coalesced write-out: 4 lanes per row, 8 rows per pass ----
+            const int vrow_self = min(max(rem, 0), DF_PER);      // valid bytes of my row in this period
+            const unsigned long long optr_self = reinterpret_cast<unsigned long long>(optr);
 #pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + (lane >> 3), col = lane & 7;
-                    const int vr = __shfl_sync(FULL, vrow_self, r);
-                    const unsigned long long dptr = __shfl_sync(FULL, optr_self, r);
-                    if (col * 16 < vr) {
-                        const uint8_t* sp = s_out + r * DF_OUT_B + col * 16;
-                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
-                        if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
-                            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
-                        } else {   // window edge or unaligned first chunk: byte stores
-                            const int nbyte = min(16, vr - col * 16);
-                            for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
-                        }
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + wrow;
+                const int vr = __shfl_sync(FULL, vrow_self, r);
+                const unsigned long long dptr = __shfl_sync(FULL, optr_self, r);
+                if (wcol * 16 < vr) {
+                    const uint8_t* sp = s_out + r * DF_OUT_B + wcol * 16;
+                    uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + wcol * 16;
+                    if (wcol * 16 + 16 <= vr && (dptr & 15) == 0) {
+                        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
+                    } else {   // window edge or unaligned first chunk: byte stores
+                        const int nbyte = min(16, vr - wcol * 16);
+                        for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
                     }
                 }
+            }
             }
             // ---- install the next period's window ----
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = i * 8 + prow;
-                uint32_t* d = s_str + r * DF_STR_W + pcol * 4;
+            for (int i = 0; i < DF_NP; ++i) {
+                uint32_t* d = s_str + prow[i] * DF_STR_W + pcol[i] * 4;
                 d[0] = bswap32(nx4[i].x); d[1] = bswap32(nx4[i].y); d[2] = bswap32(nx4[i].z); d[3] = bswap32(nx4[i].w);
             }
             __syncwarp();
             wunit = nunit;
             bp += consumed;
-            rem -= 128;
-            optr += 128;
+            rem -= DF_PER;
+            optr += DF_PER;
         }
     }
 }
