@@ -177,62 +177,59 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
 }
 
 // ---- fast decoder (NSYM = 4: codebooks with Lmax <= 2) ----
-// One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks and works in periods of
-// DF_PER = 64 symbols per lane (small periods keep the shared-memory footprint per lane at ~130 B, so
-// ~40 warps stay resident per SM and hide the LUT latency of the serial per-lane decode chain):
-//   * stream bytes reach shared memory through cooperative 16-byte loads.  The loads of period k+1 are
-//     issued at the top of period k into registers and stored at its end, so their latency hides
-//     behind a whole period of decoding.  A period consumes 64..128 bits, so the 48-byte window that
-//     starts at the 16-byte unit holding bit bp+64 always covers the next period;
+// One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks.
+//   * The kernel is bound by the LSU data pipe (shared-memory wavefronts), so everything that can stay
+//     off that pipe does: every lane stages its whole chunk of the stream (<= 272 B: 2048 bits + 16-byte
+//     alignment slack) with ONE TMA bulk copy (cp.async.bulk -> UBLKCP, mbarrier completion): no LSU
+//     wavefronts, no registers, one latency exposure per 1024 symbols per lane;
 //   * one 32-bit snapshot of the stream feeds 4 LUT lookups (<= 8 bits each, 4 symbols each, fixed
 //     output positions); the refill test runs once per 16 symbols and the refill word is read one
 //     snapshot ahead of use;
 //   * decoded symbols go to a padded shared-memory tile (64 B per lane and period) that the warp
 //     writes out with coalesced 16-byte stores (4 lanes per row).
-constexpr int DF_WARPS = 8;
+constexpr int DF_WARPS = 6;
 constexpr int DF_PER = 64;             // symbols per lane and period
-constexpr int DF_NP = 3;               // 16-byte pieces staged per lane and period
-constexpr int DF_STR_W = 13;           // staged words per lane: 12 + 1 pad (odd stride: conflict-free refills)
-constexpr int DF_STR_B = (32 * DF_STR_W * 4 + 15) / 16 * 16;
+constexpr int DF_ROW_B = 272;          // staged stream bytes per lane
+constexpr int DF_STR_B = 32 * DF_ROW_B;
 constexpr int DF_OUT_B = 80;           // output tile row: 64 B + 16 B pad
-constexpr int DF_PER_WARP = DF_STR_B + 32 * DF_OUT_B;
+constexpr int DF_PER_WARP = DF_STR_B + 32 * DF_OUT_B + 16;   // + mbarrier
 
 template <bool SMEM_LUT>
-__global__ void __launch_bounds__(DF_WARPS * 32, 5) k_decode_fast(const __grid_constant__ DecParams P) {
-    extern __shared__ __align__(16) uint8_t dsm[];
+__global__ void __launch_bounds__(DF_WARPS * 32, 3) k_decode_fast(const __grid_constant__ DecParams P) {
+    extern __shared__ __align__(128) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
     if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->Lmax > 2) return;   // host view does not match the table block
     const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DF_PER_WARP);
-    uint8_t* s_out = dsm + warp * DF_PER_WARP + DF_STR_B;
+    uint8_t* s_str = dsm + warp * DF_PER_WARP;
+    uint8_t* s_out = s_str + DF_STR_B;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + 32 * DF_OUT_B);
     const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
+    if (lane == 0) {
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
     if (SMEM_LUT) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DF_WARPS * DF_PER_WARP);
         const int nent = (T->S * K) << W;
         for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
-        __syncthreads();
     }
+    __syncthreads();
     const long long nitems = (long long)P.C * P.item_chunks;
     const long long ngroups = (nitems + 31) / 32;
-    const uint32_t slot_units = (uint32_t)(P.slot_bytes >> 4);
-    const uint32_t last_unit = (uint32_t)((long long)P.C * slot_units - 1);   // host guarantees < 2^32 units
-    const uint4* units = reinterpret_cast<const uint4*>(P.stream);
+    const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
     const int wsh = 32 - W;
-    // cooperative window load: piece p = i*32 + lane of 96 -> row p/3, column p%3
-    int prow[DF_NP], pcol[DF_NP];
-#pragma unroll
-    for (int i = 0; i < DF_NP; ++i) { const int p = i * 32 + lane; prow[i] = p / DF_NP; pcol[i] = p - prow[i] * DF_NP; }
     // write-out: 4 lanes per 64-byte row; the two rows of a quarter-warp are 4 apart (conflict-free)
     const int wrow = (lane >> 3) + 4 * ((lane >> 2) & 1), wcol = lane & 3;
+    uint32_t parity = 0;
 
     for (long long g = (long long)blockIdx.x * DF_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DF_WARPS) {
         // ---- this lane's chunk ----
         const long long item = g * 32 + lane;
         int rem = 0;
         uint32_t bp = 0;                                         // bit position in the channel's stream
-        uint32_t ubase = 0;                                      // first 16-byte unit of the channel's slot
+        const uint8_t* sbase = P.stream;
         uint8_t* optr = P.dec;
         const uint32_t* lut = SMEM_LUT ? s_lut : g_lut;
         if (item < nitems) {
@@ -245,41 +242,34 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 5) k_decode_fast(const __grid_c
                     const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
                     rem = b - a;
                     bp = P.chunk_off[(size_t)c * P.chunk_stride + j];
-                    ubase = (uint32_t)c * slot_units;
+                    sbase = P.stream + (size_t)c * P.slot_bytes;
                     optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
                     lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W;
                 }
             }
         }
-        // ---- stage the first period's window synchronously ----
-        uint32_t wunit = bp >> 7;                                // slot-relative unit where the staged window starts
+        // ---- stage the chunk's stream bytes: one TMA bulk copy per lane ----
+        const uint32_t al = (bp >> 7) << 4;                      // 16-byte aligned byte offset in the slot
+        const uint32_t nbytes = rem > 0 ? min((uint32_t)DF_ROW_B, slot_bytes - al) : 0u;
+        const uint32_t total = __reduce_add_sync(FULL, nbytes);
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < DF_NP; ++i) {
-            const uint32_t gu = __shfl_sync(FULL, ubase + wunit, prow[i]) + pcol[i];
-            const uint4 v = __ldg(units + min(gu, last_unit));
-            uint32_t* d = s_str + prow[i] * DF_STR_W + pcol[i] * 4;
-            d[0] = bswap32(v.x); d[1] = bswap32(v.y); d[2] = bswap32(v.z); d[3] = bswap32(v.w);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the rows vs. the async writes
+        if (total) {
+            if (lane == 0) mbar_expect_tx(s_bar, total);
+            __syncwarp();
+            if (nbytes) tma_load_1d(s_str + lane * DF_ROW_B, sbase + al, nbytes, s_bar);
+            mbar_wait(s_bar, parity);
+            parity ^= 1;
         }
-        __syncwarp();
+        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(s_str + lane * DF_ROW_B);
+        const uint32_t boff = bp & 127;
+        uint32_t rp = boff >> 5;
+        uint32_t hi = bswap32(rowp[rp]), lo = bswap32(rowp[rp + 1]), nx = bswap32(rowp[rp + 2]);
+        rp += 3;
+        uint32_t off = boff & 31;
 
         while (__any_sync(FULL, rem > 0)) {
-            // ---- issue the next period's window loads (consumed at the end of this period) ----
-            const uint32_t nunit = (bp + DF_PER) >> 7;
-            uint4 nx4[DF_NP];
-#pragma unroll
-            for (int i = 0; i < DF_NP; ++i) {
-                const uint32_t gu = __shfl_sync(FULL, ubase + nunit, prow[i]) + pcol[i];
-                nx4[i] = __ldg(units + min(gu, last_unit));
-            }
             // ---- DF_PER symbols per lane into the output tile ----
-            const uint32_t* rowp = s_str + lane * DF_STR_W;
-            const uint32_t boff = bp - (wunit << 7);             // 0..191
-            uint32_t rp = boff >> 5;
-            uint32_t hi = rowp[rp], lo = rowp[rp + 1], nx = rowp[rp + 2];
-            rp += 3;
-            uint32_t off = boff & 31;
-            uint32_t consumed = 0;
             uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DF_OUT_B);
 #pragma unroll
             for (int q = 0; q < DF_PER / 16; ++q) {
@@ -293,12 +283,10 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 5) k_decode_fast(const __grid_c
                     o += e >> 28;
                 }
                 off += o;
-                consumed += o;
-                if (off >= 32) { hi = lo; lo = nx; nx = rowp[rp++]; off -= 32; }
+                if (off >= 32) { hi = lo; lo = nx; nx = bswap32(rowp[min(rp, (uint32_t)(DF_ROW_B / 4 - 1))]); ++rp; off -= 32; }
                 orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
             __syncwarp();
-            {
             // ---- coalesced write-out: 4 lanes per row, 8 rows per pass ----
             const int vrow_self = min(max(rem, 0), DF_PER);      // valid bytes of my row in this period
             const unsigned long long optr_self = reinterpret_cast<unsigned long long>(optr);
@@ -318,17 +306,7 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 5) k_decode_fast(const __grid_c
                     }
                 }
             }
-            }
-            // ---- install the next period's window ----
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < DF_NP; ++i) {
-                uint32_t* d = s_str + prow[i] * DF_STR_W + pcol[i] * 4;
-                d[0] = bswap32(nx4[i].x); d[1] = bswap32(nx4[i].y); d[2] = bswap32(nx4[i].z); d[3] = bswap32(nx4[i].w);
-            }
-            __syncwarp();
-            wunit = nunit;
-            bp += consumed;
             rem -= DF_PER;
             optr += DF_PER;
         }
