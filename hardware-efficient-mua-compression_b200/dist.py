@@ -15,22 +15,30 @@ def shard_range(C, rank, world):
     return (C * rank) // world, (C * (rank + 1)) // world
 
 
-def gather_channel_report(bits, nsym, enc, peak, C_total, group=None):
-    """All ranks receive int64 [C_total, 4] = (bits, nsym, enc, peak) in global channel order."""
+def gather_channel_report(bits, nsym, enc, peak, C_total, group=None, out=None):
+    """All ranks receive int64 [C_total, 4] = (bits, nsym, enc, peak) in global channel order.
+    One collective per call; with equal shards (C_total divisible by the world size) the gathered
+    buffer is returned as is -- pass `out` (int64 [C_total, 4]) to reuse it across calls."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     local = torch.stack([bits.to(torch.int64), nsym.to(torch.int64), enc.to(torch.int64), peak.to(torch.int64)], dim=1)
     if world == 1:
         assert local.shape[0] == C_total
         return local
-    sizes = [shard_range(C_total, r, world)[1] - shard_range(C_total, r, world)[0] for r in range(world)]
     rank = dist.get_rank(group)
-    assert local.shape[0] == sizes[rank], "local shard does not match shard_range()"
+    lo, hi = shard_range(C_total, rank, world)
+    assert local.shape[0] == hi - lo, "local shard does not match shard_range()"
+    if C_total % world == 0:                                # equal shards: gather straight into the result
+        if out is None:
+            out = torch.empty((C_total, 4), dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    sizes = [shard_range(C_total, r, world)[1] - shard_range(C_total, r, world)[0] for r in range(world)]
     m = max(sizes)
     padded = torch.zeros((m, 4), dtype=torch.int64, device=local.device)
     padded[: local.shape[0]] = local
-    out = torch.empty((world * m, 4), dtype=torch.int64, device=local.device)
-    dist.all_gather_into_tensor(out, padded, group=group)
-    return torch.cat([out[r * m: r * m + sizes[r]] for r in range(world)], dim=0)
+    buf = torch.empty((world * m, 4), dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    return torch.cat([buf[r * m: r * m + sizes[r]] for r in range(world)], dim=0)
 
 
 def br_report(report, BP):
