@@ -1,0 +1,106 @@
+"""More GPU parity cases: general codec at medium size, error paths, launch hints, input loaders."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mua_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+import mua_b200  # noqa: E402
+from mua_b200 import pipeline as P, io as mio, _lib  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("S", [4, 5, 8, 10])
+def test_general_codec_medium(S, sclv_tables):
+    """2 000 channels x 6 000 bins through calibrate (all 9 history lengths) -> encode -> decode with the SCLV the
+    calibration picked: encoded length == SCLV . post histogram for every channel, lossless, streams of a sample
+    of channels identical to the oracle's."""
+    C, T = 2000, 6000
+    thr = O.synth_threshold_table(100.0)
+    rec = P.synth_recording(C, T, seed=20 + S, BP_ms=100.0, bursty=True, device=DEV, thr=thr)
+    cb = mua_b200.Codebook(S, device=DEV)
+    cal = P.calibrate(rec, cb, O.HIST_SIZES, use_sort=True, window="skip")
+    h = 4                                                        # H = 64
+    st, en, pk, ec = (cal[k][:, h] for k in ("cutoff", "end", "peak", "enc"))
+    assert int((en < 0).sum()) == 0
+    es = P.encode(rec, cb, st, en, pk, ec)
+    assert int(es.overflow.item()) == 0
+    assert torch.equal(es.total_bits, cal["bits"][:, h])
+    dec = P.decode(es, rec, cb, st, en, pk, ec, max_end=64 + T // 2)
+    assert int(P.verify(rec, dec, S, st, en).item()) == 0
+    pick = np.sort(np.random.default_rng(S).choice(C, size=12, replace=False))
+    xs = O.synth_symbols(20 + S, pick, T, thr, True)
+    for i, c in enumerate(pick):
+        c = int(c)
+        want, total, offs = O.encode_channel(xs[i], int(st[c]), int(en[c]), S, O.rank_of_symbol(int(pk[c]), S),
+                                             cb.codes[int(ec[c])], cb.lens[int(ec[c])])
+        assert int(es.total_bits[c]) == total
+        assert np.array_equal(es.channel_bytes(c), want)
+        assert np.array_equal(es.chunk_off[c].cpu().numpy().view(np.uint32)[:len(offs)], offs)
+    # the skip rule at the longest history length: H = 1024, end = 1024 + 3000 <= 6000, nothing skipped; at T = 1500 all skipped
+    short = P.Recording.from_matrix(rec.sym[:50, :1500].contiguous(), DEV)
+    cal_s = P.calibrate(short, cb, [1024], use_sort=True, window="skip", want=("end", "bits", "nsym"))
+    assert int((cal_s["end"] == -1).sum()) == 50 and int(cal_s["nsym"].sum()) == 0
+
+
+def test_overflow_flag_and_no_write_past_slot():
+    rng = np.random.default_rng(1)
+    x = rng.integers(1, 3, size=(4, 4096)).astype(np.uint8)      # all 2-bit codes: 8192 bits = 1024 B per channel
+    rec = P.Recording.from_matrix(x, DEV)
+    cb = mua_b200.Codebook(3, np.array([[1, 2, 2]]), device=DEV)
+    z = torch.zeros(4, dtype=torch.int32, device=DEV)
+    st, en = z, z + 4096
+    pk, ec = z.to(torch.uint8), z.to(torch.uint8)
+    slot = 512
+    guard = torch.full((4, slot), 0xAB, dtype=torch.uint8, device=DEV)
+    es = P.EncodedStreams(stream=guard, chunk_off=torch.zeros((4, 4), dtype=torch.int32, device=DEV),
+                          total_bits=torch.zeros(4, dtype=torch.int64, device=DEV),
+                          overflow=torch.zeros(1, dtype=torch.int32, device=DEV), slot_bytes=slot, chunk_stride=4)
+    canary = torch.full((64,), 0xCD, dtype=torch.uint8, device=DEV)
+    P.encode(rec, cb, st, en, pk, ec, out=es)
+    assert int(es.overflow.item()) == 1
+    assert int(es.total_bits[0]) == 8192                        # the bit count is still exact
+    assert bool((canary == 0xCD).all())
+    es2 = P.encode(rec, cb, st, en, pk, ec)                      # worst-case slot: fits
+    assert int(es2.overflow.item()) == 0
+
+
+def test_error_returns():
+    lib = _lib.load()
+    cb = mua_b200.Codebook(3, np.array([[1, 2, 2]]), device=DEV)
+    buf = torch.zeros(4096 + 64, dtype=torch.uint8, device=DEV)
+    rc = lib.mua_calibrate(buf.data_ptr() + 1, None, None, 1024, 1000, 4, 3, None, 1, 1, 0, cb.d_tables.data_ptr(), 1, 0,
+                           None, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"aligned" in lib.mua_last_error()
+    with pytest.raises(_lib.MuaError):
+        _lib.check(lib.mua_encode(buf.data_ptr(), None, None, 1000, 1000, 4, 3, None, None, None, None, None, 1, 2,
+                                  None, 16, None, 1, None, None, None))
+    with pytest.raises(Exception):
+        mua_b200.Codebook(3, np.array([[1, 1, 2]]), device=DEV)  # not a complete prefix code
+
+
+def test_loaders(tmp_path, recordings):
+    from scipy.io import savemat
+    all_binned, bin_vector = recordings
+    p = os.path.join(tmp_path, "all_binned_data_test.pkl")
+    mio.save_binned_pickle(p, all_binned, bin_vector)
+    abd, bv, ds = mio.load_binned_pickle(p)
+    assert bv == bin_vector and ds == ["Flint", "Sabes"]
+    recs = mio.recordings_from_binned(abd, -2, DEV)
+    assert [r.C for r in recs] == [len(all_binned[-2][0]), len(all_binned[-2][1])]
+    for c in (0, 5, 23):
+        assert np.array_equal(recs[0].channel_to_host(c), all_binned[-2][0][c])
+    # .mat as the MATLAB stage writes it: uint8 [n_bins, n_channels]
+    m = np.random.default_rng(3).poisson(0.8, size=(1234, 96)).astype(np.uint8)
+    mp = os.path.join(tmp_path, "rec_BP_50_ms.mat")
+    savemat(mp, {"binned_MUA": m})
+    rec = mio.recording_from_mat(mp, device=DEV)
+    assert rec.C == 96 and rec.T == 1234
+    assert np.array_equal(rec.sym.cpu().numpy()[:, :1234], m.T)
+    rec2 = mio.recording_from_mat(mp, device=DEV, bin_res=2, S=3)
+    assert np.array_equal(rec2.sym.cpu().numpy()[:, :617], np.minimum(O.bin_mua_data(m, 2), 2).T)
