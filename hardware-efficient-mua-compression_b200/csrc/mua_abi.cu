@@ -354,7 +354,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
         const bool fast_smem_lut = smem_lut;
         const int smem = DF_WARPS * DF_PER_WARP + (fast_smem_lut ? lut_bytes : 0);
         const long long blocks_needed = (groups + DF_WARPS - 1) / DF_WARPS;
-        const long long cap = (long long)sm_count() * 3;
+        const long long cap = (long long)sm_count() * 4;
         const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
         if (fast_smem_lut) {
             cudaError_t e = cudaFuncSetAttribute(k_decode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

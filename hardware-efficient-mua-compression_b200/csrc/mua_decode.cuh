@@ -187,15 +187,15 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
 //     snapshot ahead of use;
 //   * decoded symbols go to a padded shared-memory tile (64 B per lane and period) that the warp
 //     writes out with coalesced 16-byte stores (4 lanes per row).
-constexpr int DF_WARPS = 6;
-constexpr int DF_PER = 64;             // symbols per lane and period
+constexpr int DF_WARPS = 4;
+constexpr int DF_PER = 128;            // symbols per lane and period
 constexpr int DF_ROW_B = 272;          // staged stream bytes per lane
 constexpr int DF_STR_B = 32 * DF_ROW_B;
-constexpr int DF_OUT_B = 80;           // output tile row: 64 B + 16 B pad
+constexpr int DF_OUT_B = 144;          // output tile row: 128 B + 16 B pad
 constexpr int DF_PER_WARP = DF_STR_B + 32 * DF_OUT_B + 16;   // + mbarrier
 
 template <bool SMEM_LUT>
-__global__ void __launch_bounds__(DF_WARPS * 32, 3) k_decode_fast(const __grid_constant__ DecParams P) {
+__global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(128) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 3) k_decode_fast(const __grid_c
     const long long ngroups = (nitems + 31) / 32;
     const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
     const int wsh = 32 - W;
-    // write-out: 4 lanes per 64-byte row; the two rows of a quarter-warp are 4 apart (conflict-free)
-    const int wrow = (lane >> 3) + 4 * ((lane >> 2) & 1), wcol = lane & 3;
+    // write-out: 8 lanes per 128-byte row (one full line), 4 rows per pass
+    const int wrow = lane >> 3, wcol = lane & 7;
     uint32_t parity = 0;
 
     for (long long g = (long long)blockIdx.x * DF_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DF_WARPS) {
@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 3) k_decode_fast(const __grid_c
             const int vrow_self = min(max(rem, 0), DF_PER);      // valid bytes of my row in this period
             const unsigned long long optr_self = reinterpret_cast<unsigned long long>(optr);
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i) {
-                const int r = i * 8 + wrow;
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + wrow;
                 const int vr = __shfl_sync(FULL, vrow_self, r);
                 const unsigned long long dptr = __shfl_sync(FULL, optr_self, r);
                 if (wcol * 16 < vr) {
