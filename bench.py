@@ -215,7 +215,7 @@ def run_b200(a):
     sampler = ClockSampler(local) if rank == 0 else None
     t_w = time.perf_counter()
     nw = 0
-    while nw < max(a.warmup, 3) or (time.perf_counter() - t_w < 0.25 and nw < 200):   # >= 3 warm-up steps, >= 0.25 s under load
+    while nw < max(a.warmup, 3) or (time.perf_counter() - t_w < 1.0 and nw < 600):   # >= 3 warm-up steps, >= 1 s under load
         step()
         nw += 1
         if nw % 8 == 0:
