@@ -67,6 +67,12 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
     }
 }
 
+// sum of the four byte counters of a packed word (each <= 252)
+__device__ __forceinline__ int bytesum4(uint32_t x) {
+    const uint32_t y = (x & 0x00FF00FFu) + ((x >> 8) & 0x00FF00FFu);
+    return (int)((y & 0xFFFFu) + (y >> 16));
+}
+
 // ---------------------------------------------------------------------------------------------
 // calibrate: warp per channel
 // ---------------------------------------------------------------------------------------------
@@ -122,43 +128,75 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
     int scan_end = 0;
     for (int i = 0; i < (need_post ? nB : nH); ++i) scan_end = max(scan_end, s_bnd[warp][i]);
 
+    // Counters: per threshold v a packed word of four byte counters (flags of 4 bytes x 4 words per step,
+    // flushed into 32-bit counters before they can overflow) -- no POPC on the streaming path.
+    uint32_t accb[S];
     int acc[S];
 #pragma unroll
-    for (int v = 0; v < S; ++v) acc[v] = 0;
+    for (int v = 0; v < S; ++v) { acc[v] = 0; accb[v] = 0; }
     const int rd_end = (n + 15) & ~15;   // rows are readable up to round_up(len, 16)
-    for (int t0 = 0; t0 < scan_end; t0 += CAL_TILE) {
-        const int p0 = t0 + lane * 16;
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (p0 < rd_end) q = *reinterpret_cast<const uint4*>(row + p0);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint32_t lo7[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) lo7[j] = w[j] & 0x7F7F7F7Fu;
-        // boundaries inside (t0, t0 + CAL_TILE]
-        for (int bi = 0; bi < nB; ++bi) {
+    auto next_boundary = [&](int after) {   // smallest boundary > after that still matters (INT_MAX if none)
+        int nb_ = 0x7FFFFFFF;
+        for (int bi = 0; bi < (need_post ? nB : nH); ++bi) {
             const int b = s_bnd[warp][bi];
-            if (b > t0 && b <= t0 + CAL_TILE && (need_post || bi < nH)) {
-                const int nvalid = min(max(b - p0, 0), 16);
-                uint32_t m[4];
+            if (b > after && b < nb_) nb_ = b;
+        }
+        return nb_;
+    };
+    int nextb = next_boundary(0);
+    int since_flush = 0;
+    constexpr int UNR = 4;               // 16-byte loads in flight per lane (2 KB per warp step)
+    for (int t0 = 0; t0 < scan_end; t0 += UNR * CAL_TILE) {
+        uint4 qv[UNR];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int nb = min(max(nvalid - 4 * j, 0), 4);
-                    m[j] = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
-                }
-#pragma unroll
-                for (int v = 1; v < S; ++v) {
-                    int part = acc[v];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) part += __popc(ge_mask(w[j], lo7[j], v) & m[j]);
-                    part = warp_sum(part);
-                    if (lane == 0) s_snap[warp][bi][v] = part;
-                }
-            }
+        for (int u = 0; u < UNR; ++u) {
+            const int p0 = t0 + u * CAL_TILE + lane * 16;
+            qv[u] = make_uint4(0, 0, 0, 0);
+            if (p0 < rd_end && t0 + u * CAL_TILE < scan_end) qv[u] = *reinterpret_cast<const uint4*>(row + p0);
         }
 #pragma unroll
-        for (int v = 1; v < S; ++v) {
+        for (int u = 0; u < UNR; ++u) {
+            const int ts = t0 + u * CAL_TILE;
+            if (ts >= scan_end) break;
+            const int p0 = ts + lane * 16;
+            const uint32_t w[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
+            uint32_t lo7[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[v] += __popc(ge_mask(w[j], lo7[j], v));
+            for (int j = 0; j < 4; ++j) lo7[j] = w[j] & 0x7F7F7F7Fu;
+            if (nextb <= ts + CAL_TILE) {
+                // boundaries inside (ts, ts + CAL_TILE]: snapshot the cumulative counts (rare path)
+                for (int bi = 0; bi < nB; ++bi) {
+                    const int b = s_bnd[warp][bi];
+                    if (b > ts && b <= ts + CAL_TILE && (need_post || bi < nH)) {
+                        const int nvalid = min(max(b - p0, 0), 16);
+                        uint32_t m[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            int nb = min(max(nvalid - 4 * j, 0), 4);
+                            m[j] = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+                        }
+#pragma unroll
+                        for (int v = 1; v < S; ++v) {
+                            int part = acc[v] + bytesum4(accb[v]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) part += __popc(ge_mask(w[j], lo7[j], v) & m[j]);
+                            part = __reduce_add_sync(FULL, part);
+                            if (lane == 0) s_snap[warp][bi][v] = part;
+                        }
+                    }
+                }
+                nextb = next_boundary(ts + CAL_TILE);
+            }
+#pragma unroll
+            for (int v = 1; v < S; ++v) {
+                accb[v] += (ge_mask(w[0], lo7[0], v) >> 7) + (ge_mask(w[1], lo7[1], v) >> 7) +
+                           (ge_mask(w[2], lo7[2], v) >> 7) + (ge_mask(w[3], lo7[3], v) >> 7);
+            }
+            if (++since_flush == 63) {   // byte counters hold at most 63 * 4 = 252
+#pragma unroll
+                for (int v = 1; v < S; ++v) { acc[v] += bytesum4(accb[v]); accb[v] = 0; }
+                since_flush = 0;
+            }
         }
     }
     __syncwarp();
