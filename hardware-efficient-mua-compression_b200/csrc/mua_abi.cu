@@ -66,7 +66,7 @@ void layout_sizes(int S, int K, int Lmax, TabHdr* h) {
     h->W = h->nsym * Lmax;
     h->enc1_off = align_up((int)sizeof(TabHdr), 512);
     h->enc2_off = align_up(h->enc1_off + S * K * 16 * 4, 512);
-    int next = align_up(h->enc2_off + S * K * 256 * 8, 512);
+    int next = align_up(h->enc2_off + S * K * 256 * 4, 512);
     h->enc4_off = 0;
     if (Lmax <= 2) {
         h->enc4_off = next;

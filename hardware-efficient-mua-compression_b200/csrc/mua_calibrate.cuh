@@ -31,13 +31,13 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
         T->idx[p][tid] = tid < S ? s_idx[tid] : 0;
     }
     uint32_t* enc1 = reinterpret_cast<uint32_t*>(blob + T->enc1_off) + (size_t)(p * K + k) * 16;
-    uint2* enc2 = reinterpret_cast<uint2*>(blob + T->enc2_off) + (size_t)(p * K + k) * 256;
+    uint32_t* enc2 = reinterpret_cast<uint32_t*>(blob + T->enc2_off) + (size_t)(p * K + k) * 256;
     uint32_t* dec = reinterpret_cast<uint32_t*>(blob + T->dec_off) + ((size_t)(p * K + k) << W);
     if (tid < 16) enc1[tid] = ((uint32_t)s_len[s_rank[tid]] << 16) | s_code[s_rank[tid]];
     {
         int r0 = s_rank[tid & 15], r1 = s_rank[tid >> 4];
         uint32_t l1 = s_len[r1];
-        enc2[tid] = make_uint2(((uint32_t)s_code[r0] << l1) | s_code[r1], (uint32_t)s_len[r0] + l1);
+        enc2[tid] = (((uint32_t)s_code[r0] << l1) | s_code[r1]) | (((uint32_t)s_len[r0] + l1) << 24);
     }
     if (T->enc4_off) {   // Lmax <= 2: four 2-bit symbols per entry
         uint16_t* enc4 = reinterpret_cast<uint16_t*>(blob + T->enc4_off) + (size_t)(p * K + k) * 256;

@@ -32,10 +32,9 @@ struct DecParams {
 //   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
 //     writes out with coalesced 16-byte stores.
 constexpr int DG_WARPS = 4;
-constexpr int DG_STR_W = 69;          // staged stream words per lane (68 used + 1 pad: odd stride, no bank conflicts)
-constexpr int DG_STR_PIECES = 17;     // 16-byte pieces staged per lane: 272 B = 128 bits of alignment slack + 2048 bits
+constexpr int DG_STR_W = 68;          // staged stream words per lane: 272 B = 128 bits of alignment slack + 2048 bits
 constexpr int DG_OUT_B = 144;         // output tile row: 128 B + 16 B pad
-constexpr int DG_PER_WARP = 32 * DG_STR_W * 4 + 32 * DG_OUT_B;
+constexpr int DG_PER_WARP = 32 * DG_STR_W * 4 + 32 * DG_OUT_B + 16;   // + mbarrier
 
 template <int NSYM, bool SMEM_LUT>
 __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_constant__ DecParams P) {
@@ -47,13 +46,19 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DG_PER_WARP);
     uint8_t* s_out = dsm + warp * DG_PER_WARP + 32 * DG_STR_W * 4;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + 32 * DG_OUT_B);
     const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DG_WARPS * DG_PER_WARP);
+    if (lane == 0) {
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
     if (SMEM_LUT) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DG_WARPS * DG_PER_WARP);
         const int nent = (T->S * K) << W;
         for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
-        __syncthreads();
     }
+    __syncthreads();
+    uint32_t parity = 0;
     const int periods_per_stage = 2048 / (128 * T->Lmax);        // 128-symbol periods one staged row is good for
     const long long nitems = (long long)P.C * P.item_chunks;
     const long long ngroups = (nitems + 31) / 32;
@@ -85,27 +90,23 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
         }
         int done = 0;                                            // symbols already written out
         while (__any_sync(FULL, rem > 0)) {
-            // ---- stage 272 stream bytes per lane, starting at the 16-byte unit holding `bitpos` ----
+            // ---- stage 272 stream bytes per lane (one TMA bulk copy each), from the 16-byte unit holding `bitpos` ----
             const uint32_t cur_al = (bitpos >> 7) << 4;
-            const unsigned long long src_lane = reinterpret_cast<unsigned long long>(sbase) + cur_al;
+            const uint32_t nbytes = rem > 0 ? min((uint32_t)(DG_STR_W * 4), slot_bytes - cur_al) : 0u;
+            const uint32_t total = __reduce_add_sync(FULL, nbytes);
             __syncwarp();
-#pragma unroll 1
-            for (int i = 0; i < DG_STR_PIECES; ++i) {
-                const int p = i * 32 + lane;
-                const int r = p / DG_STR_PIECES, col = p - r * DG_STR_PIECES;
-                const unsigned long long src = __shfl_sync(FULL, src_lane, r);
-                const uint32_t al_r = __shfl_sync(FULL, cur_al, r);
-                const int rem_r = __shfl_sync(FULL, rem, r);
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (rem_r > 0 && al_r + col * 16 + 16 <= slot_bytes) v = __ldg(reinterpret_cast<const uint4*>(src) + col);
-                uint32_t* d = s_str + r * DG_STR_W + col * 4;
-                d[0] = bswap32(v.x); d[1] = bswap32(v.y); d[2] = bswap32(v.z); d[3] = bswap32(v.w);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (total) {
+                if (lane == 0) mbar_expect_tx(s_bar, total);
+                __syncwarp();
+                if (nbytes) tma_load_1d(s_str + lane * DG_STR_W, sbase + cur_al, nbytes, s_bar);
+                mbar_wait(s_bar, parity);
+                parity ^= 1;
             }
-            __syncwarp();
             const uint32_t* rowp = s_str + lane * DG_STR_W;
             const uint32_t boff = bitpos - cur_al * 8;           // 0..127
             uint32_t rp = boff >> 5;
-            uint32_t hi = rowp[rp], lo = rowp[rp + 1];
+            uint32_t hi = bswap32(rowp[rp]), lo = bswap32(rowp[rp + 1]);
             rp += 2;
             uint32_t off = boff & 31;
             uint32_t consumed = 0;                               // bits consumed in this stage
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
                         }
                         off += o;
                         consumed += o;
-                        if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
+                        if (off >= 32) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(DG_STR_W - 1))]); ++rp; off -= 32; }
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
                                 const uint32_t used = e >> 28;
                                 off += used;
                                 consumed += used;
-                                if (off >= 32) { hi = lo; lo = rowp[rp++]; off -= 32; }
+                                if (off >= 32) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(DG_STR_W - 1))]); ++rp; off -= 32; }
                             }
                             ow[k] = wsym;
                         }

@@ -356,8 +356,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_
 struct EncGenSmem {
     static constexpr int RW = 512;                              // 1024 symbols * 9 bits = 288 words + slack
     static constexpr int IN = 0;
-    static constexpr int LUT2 = IN + ENC_NST * TILE;            // 256 * 8
-    static constexpr int LUT1 = LUT2 + 2048;                    // 16 * 4
+    static constexpr int LUT2 = IN + ENC_NST * TILE;            // 256 * 4
+    static constexpr int LUT1 = LUT2 + 1024;                    // 16 * 4
     static constexpr int RING = LUT1 + 64;
     static constexpr int BARS = RING + RW * 4;
     static constexpr int PER_WARP = (BARS + ENC_NST * 8 + 127) / 128 * 128;
@@ -404,9 +404,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 2) k_encode_gen(const __grid_c
             const int combo = (int)P.peak[c] * K + (int)P.enc[c];
             if (combo != cur_combo) {
                 __syncwarp();
-                const uint4* src = g_enc2 + (size_t)combo * 128;
+                const uint4* src = g_enc2 + (size_t)combo * 64;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(s_lut2)[lane + 32 * i] = src[lane + 32 * i];
+                for (int i = 0; i < 2; ++i) reinterpret_cast<uint4*>(s_lut2)[lane + 32 * i] = src[lane + 32 * i];
                 if (lane < 16) s_lut1[lane] = g_enc1[(size_t)combo * 16 + lane];
                 cur_combo = combo;
                 __syncwarp();
@@ -443,8 +443,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 2) k_encode_gen(const __grid_c
                 const int p0 = ts + lane * 32;
                 const int vlo = max(start - p0, 0), vhi = min(end - p0, 32);   // valid symbols [vlo, vhi)
 
-                // pass 1: bits this lane will emit
+                // pass 1: look every symbol pair up once (code | len << 24) and count the bits this lane will emit
                 uint32_t nb = 0;
+                uint32_t pe[16];
                 if (full) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -453,11 +454,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 2) k_encode_gen(const __grid_c
                             uint32_t h4 = wj & 0xF0F0F0F0u, t1 = h4 | (h4 >> 1);
                             t1 |= t1 >> 2;
                             wj = (wj | (((t1 >> 4) & 0x01010101u) * 0xFFu)) & 0x0F0F0F0Fu;
-                            w[j] = wj;
                         }
-                        const uint32_t y = ((wj << 3) | (wj >> 1)) & 0x07F807F8u;
-                        nb += reinterpret_cast<const uint2*>(s_lut2 + (y & 0xFFFFu))->y;
-                        nb += reinterpret_cast<const uint2*>(s_lut2 + (y >> 16))->y;
+                        const uint32_t y = ((wj << 2) | (wj >> 2)) & 0x03FC03FCu;   // two byte offsets of 4-byte entries
+                        pe[2 * j] = *reinterpret_cast<const uint32_t*>(s_lut2 + (y & 0xFFFFu));
+                        pe[2 * j + 1] = *reinterpret_cast<const uint32_t*>(s_lut2 + (y >> 16));
+                        nb += (pe[2 * j] >> 24) + (pe[2 * j + 1] >> 24);
                     }
                 } else {
                     for (int i = vlo; i < vhi; ++i) nb += s_lut1[min((uint32_t)tile[i], 15u)] >> 16;
@@ -486,13 +487,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 2) k_encode_gen(const __grid_c
                 };
                 if (full) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t y = ((w[j] << 3) | (w[j] >> 1)) & 0x07F807F8u;
-                        const uint2 e0 = *reinterpret_cast<const uint2*>(s_lut2 + (y & 0xFFFFu));
-                        const uint2 e1 = *reinterpret_cast<const uint2*>(s_lut2 + (y >> 16));
-                        append(e0.x, (int)e0.y);
-                        append(e1.x, (int)e1.y);
-                    }
+                    for (int j = 0; j < 16; ++j) append(pe[j] & 0xFFFFFFu, (int)(pe[j] >> 24));
                 } else {
                     for (int i = vlo; i < vhi; ++i) {
                         const uint32_t e1 = s_lut1[min((uint32_t)tile[i], 15u)];
