@@ -2,7 +2,8 @@
 path).  Python host code -> ctypes -> libmua_b200.so (hand-written sm_100a kernels); PyTorch is used
 only for device memory, streams and torch.distributed.  There is no CPU fallback."""
 from . import _lib  # noqa: F401
-from .codebook import Codebook, load_sclv_tables, canonical_codes  # noqa: F401
+from .codebook import Codebook, load_sclv_tables, canonical_codes, generator_codes  # noqa: F401
+from . import sclv_gen  # noqa: F401
 from . import io  # noqa: F401
 from .pipeline import (Recording, calibrate, train_hist, select_sclv, bit_counts, elim_scores, encode, decode,  # noqa: F401
                        verify, bin_raster, synth_recording, synth_threshold_table, EncodedStreams)

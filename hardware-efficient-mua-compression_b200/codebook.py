@@ -40,6 +40,15 @@ def canonical_codes(lens):
     return codes
 
 
+def generator_codes(S):
+    """Codewords the reference's SCLV generator emits for each row of the S table (rank order), as integers
+    [K, S] -- e.g. S=5 gives the FPGA case table of `FPGA implementation/5_encoder_3.v:15-47`; S=3 gives
+    '1','00','01' (the bit-polarity twin of test_chosen_system.py:26)."""
+    with open(os.path.join(os.path.dirname(_DATA), "sclv_generator_codebooks.json")) as f:
+        books = json.load(f)["codebooks"][str(int(S))]
+    return np.array([[int(c, 2) for c in row] for row in books], dtype=np.int64)
+
+
 class Codebook:
     """Device table block for one alphabet size S: SCLV rows, codewords, encode/decode LUTs."""
 
@@ -54,6 +63,10 @@ class Codebook:
         lens8 = np.ascontiguousarray(self.lens, dtype=np.uint8)
         if codes is None:
             codes = canonical_codes(lens8)
+        elif isinstance(codes, str):
+            assert codes == "generator" and lens is not None
+            codes = generator_codes(self.S)
+            assert codes.shape == self.lens.shape, "generator codebooks exist for the full SCLV tables only"
         self.codes = np.ascontiguousarray(np.atleast_2d(codes), dtype=np.int64)
         codes16 = np.ascontiguousarray(self.codes, dtype=np.uint16)
         lib = _lib.load()

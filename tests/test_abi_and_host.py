@@ -107,3 +107,21 @@ def test_shard_range_covers_everything():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_sclv_generator_reproduces_reference_tables():
+    """mua_b200.sclv_gen regenerates every Stored_SCLVs_S_<S>.pkl (rows and row order) and the generator's
+    codeword strings: S=5 == the FPGA case table (5_encoder_3.v:15-47), S=3 == '1','00','01' (SURVEY B.3)."""
+    from mua_b200 import sclv_gen
+    from oracle import mua_oracle as O
+    t = mua_b200.load_sclv_tables()
+    for S in range(2, 11):
+        rows, books = sclv_gen.generate(S)
+        assert np.array_equal(np.array(rows), t[S]), S
+        for row, book in zip(rows, books):
+            assert [len(c) for c in book] == row
+            for i, a in enumerate(book):                          # prefix free
+                assert all(i == j or not b.startswith(a) for j, b in enumerate(book))
+        assert np.array_equal(mua_b200.generator_codes(S), np.array([[int(c, 2) for c in b] for b in books]))
+    assert sclv_gen.generate(5)[1] == O.GENERATOR_CODEBOOK_S5
+    assert sclv_gen.generate(3)[1] == [["1", "00", "01"]]

@@ -104,3 +104,25 @@ def test_loaders(tmp_path, recordings):
     assert np.array_equal(rec.sym.cpu().numpy()[:, :1234], m.T)
     rec2 = mio.recording_from_mat(mp, device=DEV, bin_res=2, S=3)
     assert np.array_equal(rec2.sym.cpu().numpy()[:, :617], np.minimum(O.bin_mua_data(m, 2), 2).T)
+
+
+@pytest.mark.parametrize("S", [3, 5, 8])
+def test_generator_codebooks_roundtrip(S, sclv_tables):
+    """The reference generator's own codewords (non-canonical) as the codebook: streams == oracle, lossless."""
+    rng = np.random.default_rng(40 + S)
+    lens = sclv_tables[S]
+    codes = mua_b200.generator_codes(S)
+    cb = mua_b200.Codebook(S, lens, codes="generator", device=DEV)
+    assert np.array_equal(cb.codes, codes)
+    chans = [rng.poisson(0.8 + 0.3 * i, size=3000 + 17 * i).astype(np.uint8) for i in range(12)]
+    rec = P.Recording.from_channels(chans, DEV)
+    cal = P.calibrate(rec, cb, [64], use_sort=True, window="truncate")
+    st, en, pk, ec = (cal[k][:, 0] for k in ("cutoff", "end", "peak", "enc"))
+    es = P.encode(rec, cb, st, en, pk, ec)
+    dec = P.decode(es, rec, cb, st, en, pk, ec)
+    assert int(P.verify(rec, dec, S, st, en).item()) == 0 and int(es.overflow.item()) == 0
+    assert torch.equal(es.total_bits, cal["bits"][:, 0])
+    for c, x in enumerate(chans):
+        k = int(ec[c])
+        want, total, offs = O.encode_channel(x, int(st[c]), int(en[c]), S, O.rank_of_symbol(int(pk[c]), S), codes[k], lens[k])
+        assert int(es.total_bits[c]) == total and np.array_equal(es.channel_bytes(c), want)
