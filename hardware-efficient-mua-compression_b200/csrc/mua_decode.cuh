@@ -38,7 +38,7 @@ constexpr int DG_PER_WARP = 32 * DG_STR_W * 4 + 32 * DG_OUT_B + 16;   // + mbarr
 
 template <int NSYM, bool SMEM_LUT>
 __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_constant__ DecParams P) {
-    extern __shared__ __align__(16) uint8_t dsm[];
+    extern __shared__ __align__(128) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
     if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != NSYM) return;   // host view does not match the table block
