@@ -363,7 +363,7 @@ struct EncGenSmem {
     static constexpr int PER_WARP = (BARS + ENC_NST * 8 + 127) / 128 * 128;
 };
 
-__global__ void __launch_bounds__(ENC_WARPS * 32, 2) k_encode_gen(const __grid_constant__ EncParams P) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_constant__ EncParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = EncGenSmem;
     constexpr uint32_t RM = SM::RW - 1;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 2) k_encode_gen(const __grid_c
                 } else {
                     for (int i = vlo; i < vhi; ++i) nb += s_lut1[min((uint32_t)tile[i], 15u)] >> 16;
                 }
-                const uint32_t incl = warp_incl_scan(nb, lane);
+                const uint32_t incl = warp_incl_scan_p(nb);
                 const uint32_t Pnew = Pbits + __shfl_sync(FULL, incl, 31);
                 const uint32_t a = Pbits + incl - nb;
                 const uint32_t Wi = a >> 5;
@@ -495,7 +495,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 2) k_encode_gen(const __grid_c
                     }
                 }
                 const uint32_t tl = fill > 0 ? (uint32_t)(pend >> 32) : 0u;
-                const uint32_t incoming = tails_segmented(tl, nemit > 0, carry, lane);
+                uint32_t incoming;
+                if (full) {   // 32 symbols of >= 1 bit: every lane completes a word, the partial word comes from the previous lane
+                    incoming = __shfl_up_sync(FULL, tl, 1);
+                    if (lane == 0) incoming = carry;
+                    carry = __shfl_sync(FULL, tl, 31);
+                } else {
+                    incoming = tails_segmented(tl, nemit > 0, carry, lane);
+                }
                 if (nemit > 0) s_ring[Wi & RM] = first | incoming;
 
                 __syncwarp();
