@@ -201,8 +201,8 @@ int mua_bin_raster(const void* d_raster, int dtype, int64_t T0, int32_t C, int32
         REQUIRE(sym_stride >= nb, "sym_stride < number of bins");
         REQUIRE(nb <= (int64_t)65535 * BIN_TB, "too many bins for one launch");
         dim3 grid((C + BIN_TC - 1) / BIN_TC, (unsigned)((nb + BIN_TB - 1) / BIN_TB));
-        const bool al = aligned16(d_sym) && (sym_stride % 16 == 0);
-        k_bin_sym<<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_sym, al ? sym_stride : sym_stride, S ? S - 1 : 255);
+        REQUIRE(aligned16(d_sym) || sym_stride % 16 != 0, "d_sym must be 16-byte aligned when sym_stride is a multiple of 16");
+        k_bin_sym<<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_sym, sym_stride, S ? S - 1 : 255);
         CHECK_LAUNCH("k_bin_sym");
     }
     return MUA_OK;

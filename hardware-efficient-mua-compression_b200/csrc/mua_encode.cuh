@@ -34,16 +34,6 @@ struct EncParams {
 constexpr int ENC_WARPS = 8;
 constexpr int ENC_NST = 4;   // TMA stages per warp
 
-// inclusive warp scan
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
 // Partial words between lanes when some lanes emit no complete word (masked head/tail tiles):
 // segmented inclusive OR-scan of the lanes' trailing partial words; a lane that completed a word
 // (`emits`) starts a new segment.  Returns the partial word arriving at this lane; updates carry.
