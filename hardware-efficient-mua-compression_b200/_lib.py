@@ -35,6 +35,7 @@ SIGNATURES = {
     "mua_verify": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mua_online_histogram": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "mua_approx_sort": (C.c_int, [_vp, C.c_int, _i32, _i64, _vp, _vp]),
+    "mua_copy_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "mua_synth": (C.c_int, [_vp, _i64, _i32, _i32, _i64, _u32, _vp, _i32, _vp]),
 }
 

@@ -421,6 +421,18 @@ int mua_approx_sort(const void* d_hist, int dtype, int32_t n, int64_t count, int
     return MUA_OK;
 }
 
+int mua_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t rows, int32_t direction,
+                  void* stream) {
+    REQUIRE(dst && src, "NULL argument");
+    REQUIRE(width >= 0 && rows >= 0 && dst_pitch >= width && src_pitch >= width, "bad pitch/width/rows");
+    REQUIRE(direction == 0 || direction == 1, "direction must be 0 (H2D) or 1 (D2H)");
+    if (width == 0 || rows == 0) return MUA_OK;
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)rows,
+                                      direction == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy2DAsync");
+    return MUA_OK;
+}
+
 int mua_synth(uint8_t* d_sym, int64_t stride, int32_t T, int32_t C, int64_t c0, uint32_t seed, const uint32_t* d_thr, int32_t bursty,
               void* stream) {
     REQUIRE(d_sym && d_thr, "NULL argument");

@@ -80,6 +80,18 @@ class Recording:
         return cls(sym=host.to(device, non_blocking=True), C=len(lens), T=int(lens.max()) if len(lens) else 0, stride=0,
                    off=torch.from_numpy(offs).to(device), len=torch.from_numpy(lens.astype(np.int32)).to(device))
 
+    def upload_rows(self, host: torch.Tensor, width: Optional[int] = None):
+        """Host -> device copy of the first `width` bytes of every row of a (pinned) uint8 [C, >=width] host
+        tensor into this uniform recording (mua_copy_rows / cudaMemcpy2DAsync on the current stream).  The path
+        only reads bins [0, cutoff + len/2), so `width = round_up(H + T//2, 16)` is all it needs."""
+        assert self.uniform and host.dtype == torch.uint8 and host.dim() == 2 and host.shape[0] >= self.C
+        width = self.stride if width is None else int(width)
+        assert width <= self.stride and width <= host.stride(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mua_copy_rows(_ptr(self.sym), int(self.stride), C.c_void_p(host.data_ptr()), int(host.stride(0)),
+                                                 width, int(self.C), 0, _stream()))
+        return self
+
     def layout_args(self):
         return (_ptr(self.sym), _ptr(self.off), _ptr(self.len), int(self.stride), int(self.T), int(self.C))
 

@@ -178,6 +178,14 @@ int mua_online_histogram(uint8_t* d_x, int64_t n, int64_t H, int32_t max_firing_
 int mua_approx_sort(const void* d_hist, int dtype, int32_t n, int64_t count, int64_t* d_idx,
                     void* stream);
 
+/* ---- host <-> device row copies (for callers that keep recordings in host memory) ----------- */
+
+/* Copy `rows` rows of `width` bytes between pitched buffers (cudaMemcpy2DAsync on `stream`).
+ * direction: 0 = host -> device, 1 = device -> host.  The path only reads bins [0, cutoff + len/2) of a
+ * channel (test_chosen_system.py:99-103), so a caller uploads just that prefix of every row. */
+int mua_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
+                  int64_t rows, int32_t direction, void* stream);
+
 /* ---- synthetic MUA (bench/test input; integer-only counter RNG, mirrored by the oracle) ---- */
 
 /* d_sym[c][t] for c in [c0, c0+C): see oracle/mua_oracle.py:synth_symbols.  d_thr: uint32 [256][24]. */
