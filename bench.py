@@ -403,7 +403,17 @@ def run_e2e(a, rec, cb, dev, world, rank):
                    "from one pinned block of the synthetic stream" % (nblk_eff, nb)}
 
 
+def _protect_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the JSON line is the only
+    thing written to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _protect_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
