@@ -126,3 +126,42 @@ def test_generator_codebooks_roundtrip(S, sclv_tables):
         k = int(ec[c])
         want, total, offs = O.encode_channel(x, int(st[c]), int(en[c]), S, O.rank_of_symbol(int(pk[c]), S), codes[k], lens[k])
         assert int(es.total_bits[c]) == total and np.array_equal(es.channel_bytes(c), want)
+
+
+def test_dropin_level0_script_loop(recordings):
+    """Level-0 drop-in: a per-channel loop with the call pattern of test_chosen_system.py:66-125 (clip, calibration
+    length from online_histogram_w_sat_based_nb_of_samples, np.histogram of the two windows, approx_sort, mapped
+    histogram . SCLV) written against `from functions_1 import *` of the shim -> the reference script's BR list."""
+    import subprocess, sys, json, textwrap
+    from conftest import ROOT, GOLDEN
+    code = textwrap.dedent('''
+        import sys, json
+        sys.path.insert(0, %r)
+        sys.path.insert(0, %r)
+        from functions_1 import *
+        import numpy as np
+        z = np.load(%r, allow_pickle=True)
+        S, H, BP, SCLV = 3, 64, 50, [1, 2, 2]
+        BR = []
+        for ds in range(2):
+            keys = sorted(k for k in z.files if k.startswith("bp50_ds%%d_ch" %% ds))
+            chans = [z[k].copy() for k in keys]
+            edges = np.arange(-0.5, S + 0.5, 1)
+            avg = np.zeros(len(chans))
+            for c, x in enumerate(chans):
+                x[x > S - 1] = S - 1
+                _, cutoff = online_histogram_w_sat_based_nb_of_samples(x, H, S - 1)
+                h_assign = np.histogram(x[:int(cutoff)], edges)[0]
+                idx, _ = approx_sort(h_assign)
+                end = int(cutoff) + int(len(x) / 2)
+                h_post = np.histogram(x[int(cutoff):end], edges)[0]
+                mapped = np.array([h_post[i] for i in idx])
+                avg[c] = np.matmul(mapped, np.transpose(SCLV)) / np.sum(mapped)
+            BR.append(np.mean(avg) / (BP / 1000))
+        print(json.dumps([float(b).hex() for b in BR]))
+    ''') % (os.path.join(ROOT, "hardware-efficient-mua-compression_b200", "dropin"), ROOT, os.path.join(GOLDEN, "recordings.npz"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = [float.fromhex(h) for h in json.loads(out.stdout.strip().splitlines()[-1])]
+    want = np.load(os.path.join(GOLDEN, "chosen_system.npz"))["BR"]
+    assert np.array(got, dtype=np.float64).tobytes() == want[:2].tobytes()
