@@ -309,11 +309,13 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     P.total_bits = d_total_bits; P.overflow = d_overflow;
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
     if (h.Lmax <= 2) {
-        const int smem = EncFastSmem::PER_WARP * ENC_WARPS;
+        const int smem = EncFastSmem::PER_WARP * EF_WARPS;
         cudaError_t e = cudaFuncSetAttribute(k_encode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");
-        const int grid = ctas_needed < sm_count() * 4 ? ctas_needed : sm_count() * 4;
-        k_encode_fast<<<grid, ENC_WARPS * 32, smem, st>>>(P);
+        const int per_sm = EF_NG == 2 ? 4 : 5;
+        const int need = (C + EF_WARPS - 1) / EF_WARPS;
+        const int grid = need < sm_count() * per_sm ? need : sm_count() * per_sm;
+        k_encode_fast<<<grid, EF_WARPS * 32, smem, st>>>(P);
     } else {
         const int smem = EncGenSmem::PER_WARP * ENC_WARPS;
         cudaError_t e = cudaFuncSetAttribute(k_encode_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

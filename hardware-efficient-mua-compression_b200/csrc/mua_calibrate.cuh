@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
         enc2[tid] = (((uint32_t)s_code[r0] << l1) | s_code[r1]) | (((uint32_t)s_len[r0] + l1) << 24);
     }
     if (T->enc4_off) {   // Lmax <= 2: four 2-bit symbols per entry
-        uint16_t* enc4 = reinterpret_cast<uint16_t*>(blob + T->enc4_off) + (size_t)(p * K + k) * 256;
+        uint8_t* enc4 = blob + T->enc4_off + (size_t)(p * K + k) * 512;   // [0,256): codes, [256,512): lengths
         uint32_t code = 0, len = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
             code = (code << s_len[r]) | s_code[r];
             len += s_len[r];
         }
-        enc4[tid] = (uint16_t)(code | (len << 8));
+        enc4[tid] = (uint8_t)code;
+        enc4[256 + tid] = (uint8_t)len;
     }
     const int nsym = T->nsym;
     for (int v = tid; v < (1 << W); v += blockDim.x) {

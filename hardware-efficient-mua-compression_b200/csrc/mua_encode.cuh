@@ -91,13 +91,18 @@ __device__ __forceinline__ void flush_last(const uint32_t* s_ring, uint8_t* out,
 }
 
 // ---------------------------------------------------------------------------------------------
-// fast encoder (Lmax <= 2): 2048-symbol tiles, 64 symbols (two 32-symbol halves) per lane
+// fast encoder (Lmax <= 2): EF_NG groups of 32 symbols per lane and tile
 // ---------------------------------------------------------------------------------------------
-constexpr int ETILE = 2 * TILE;        // symbols per warp tile of the fast encoder (= 2 decode chunks)
-constexpr int EF_NST = 2;              // TMA stages per warp (2 KB each)
+#ifndef MUA_EF_NG
+#define MUA_EF_NG 2
+#endif
+constexpr int EF_NG = MUA_EF_NG;       // 32-symbol groups per lane: 2 -> 2048-symbol tiles, 4 -> 4096-symbol tiles
+constexpr int ETILE = EF_NG * TILE;    // symbols per warp tile of the fast encoder (EF_NG decode chunks)
+constexpr int EF_NST = 2;              // TMA stages per warp
+constexpr int EF_WARPS = EF_NG == 2 ? 8 : 4;   // warps per CTA
 
 struct EncFastSmem {
-    static constexpr int RW = 256;                              // staging ring words (4096 bits/tile + slack)
+    static constexpr int RW = EF_NG == 2 ? 256 : 512;           // staging ring words (2*ETILE bits per tile + slack)
     static constexpr int IN = 0;                                // EF_NST * ETILE bytes
     static constexpr int LUT4 = IN + EF_NST * ETILE;            // 256 * 2, 512-byte aligned
     static constexpr int LUT1 = LUT4 + 512;                     // 16 * 4
@@ -116,28 +121,37 @@ __device__ __forceinline__ uint32_t warp_incl_scan_p(uint32_t v) {
     return v;
 }
 
-__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
     uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8_256(uint32_t saddr) {   // same index, second table (+256 bytes)
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+256];" : "=r"(v) : "r"(saddr));
     return v;
 }
 
-// 16 symbols (one uint4) -> code bits (right aligned, <= 32) and bit count (16..32): SWAR saturate to
-// S-1 (5 ops per 4 symbols), gather the four 2-bit symbols of a word into an 8-bit index with one
-// multiply, one 16-bit LUT read per word (code | len << 8), shift/or tree.
+// 16 symbols (one uint4) -> code bits (right aligned, <= 32) and bit count (16..32).  The kernel is bound by the
+// ALU pipe, so the per-word work is cut to 3 ALU ops (+2 on the FMA pipe, 2 byte loads):
+//   g   = w + satk            (FMA pipe)  bit 7 of a byte set  <=>  byte > S-1   (bytes < 129: checked per tile)
+//   m   = prmt.msb(g)         (ALU)       0xFF in those bytes
+//   ws  = lop3(w, m, satv)    (ALU)       min(byte, S-1): four 2-bit symbols
+//   p   = ws * 0x01041040     (FMA pipe)  gathers them into the top byte: q0 | q1<<2 | q2<<4 | q3<<6
+//   adr = prmt(p, lut)        (ALU)       LUT base (256-byte aligned) with its low byte replaced by the index
+//   code = lut[adr], len = lut[adr + 256] (two byte loads: no unpacking)
 __device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uint32_t satk, uint32_t satv, uint32_t& code,
                                          uint32_t& len) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t qc[4], ql[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t lo7 = w[j] & 0x7F7F7F7Fu;
-        const uint32_t g = (lo7 + satk) | w[j];                  // bit 7 of a byte: value > S-1
-        const uint32_t m = byte_msb_mask(g);                      // 0xFF where bit 7 is set
-        const uint32_t ws = (w[j] & ~m) | (satv & m);             // min(byte, S-1): 2-bit symbols
-        const uint32_t e = lds_u16((((ws * 0x01041040u) >> 23) & 0x1FEu) | lut4_saddr);
-        qc[j] = e & 0xFFu;
-        ql[j] = e >> 8;
+        const uint32_t g = w[j] + satk;
+        const uint32_t m = byte_msb_mask(g);
+        const uint32_t ws = (w[j] & ~m) | (satv & m);
+        const uint32_t adr = __byte_perm(ws * 0x01041040u, lut4_saddr, 0x7653);
+        qc[j] = lds_u8(adr);
+        ql[j] = lds_u8_256(adr);
     }
     qc[0] = (qc[0] << ql[1]) | qc[1]; ql[0] += ql[1];
     qc[2] = (qc[2] << ql[3]) | qc[3]; ql[2] += ql[3];
@@ -145,98 +159,122 @@ __device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uin
     len = ql[0] + ql[2];
 }
 
-// One tile of the fast encoder.  FULLT: the whole tile lies inside the window (every lane emits >= 64 bits).
-template <bool FULLT, uint32_t RM>
+// bytes >= 128 would carry in `w + satk`: clamp them to 127 first (they saturate to S-1 anyway)
+__device__ __forceinline__ uint4 clamp127(uint4 q) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = (w[j] | (byte_msb_mask(w[j]) & 0x7F7F7F7Fu)) & 0x7F7F7F7Fu;
+    return q;
+}
+
+// One tile of the fast encoder.  FULLT: the whole tile lies inside the window (every 32-symbol group emits
+// 32..64 bits).  The lane's 32*NG bytes are 2*NG 16-byte pieces; with a lane stride of 32*NG bytes, reading
+// piece k in every lane would be a bank conflict, so lane l reads piece (k + rot) mod 2NG (rot from the lane
+// index: conflict-free) and a log2(2NG)-level select network puts the results back in order.
+template <bool FULLT, uint32_t RM, int NG>
 __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4_saddr, const uint32_t* s_lut1, uint32_t satk,
                                               uint32_t satv, int ts, int start, int end, int lane, uint32_t* s_ring,
                                               uint32_t& Pbits, uint32_t& carry, uint32_t& a_lane) {
-    // The lane's 64 bytes are four 16-byte pieces.  With a 64-byte lane stride, reading piece k in
-    // every lane would be a 4-way bank conflict; lane l reads piece (k + rot) & 3, rot = (l >> 1) & 3,
-    // which is conflict-free, and a two-level select network puts the four results back in order.
-    const uint32_t rot = (lane >> 1) & 3;
-    uint32_t pc[4], pl[4];
+    constexpr int NP = 2 * NG;
+    const uint32_t rot = NG == 2 ? ((lane >> 1) & 3) : (lane & 7);
+    uint32_t pc[NP], pl[NP];
+    uint4 qv[NP];
+    uint32_t any_hi = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        encode16(*reinterpret_cast<const uint4*>(tile + 16 * ((k + rot) & 3)), lut4_saddr, satk, satv, pc[k], pl[k]);
-    {
-        const bool r1 = rot & 1, r2 = rot & 2;
-        uint32_t tc[4], tl4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { tc[j] = r1 ? pc[(j + 3) & 3] : pc[j]; tl4[j] = r1 ? pl[(j + 3) & 3] : pl[j]; }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { pc[j] = r2 ? tc[(j + 2) & 3] : tc[j]; pl[j] = r2 ? tl4[(j + 2) & 3] : tl4[j]; }
+    for (int k = 0; k < NP; ++k) {
+        qv[k] = *reinterpret_cast<const uint4*>(tile + 16 * ((k + rot) & (NP - 1)));
+        any_hi |= (qv[k].x | qv[k].y) | (qv[k].z | qv[k].w);
     }
-    unsigned long long acc0 = ((unsigned long long)pc[0] << pl[1]) | pc[1];
-    unsigned long long acc1 = ((unsigned long long)pc[2] << pl[3]) | pc[3];
-    uint32_t nb0 = pl[0] + pl[1], nb1 = pl[2] + pl[3];           // 32..64 bits each
-    if (!FULLT) {
-        // head/tail tile: a half outside the window emits nothing; a half cut by the window boundary is
-        // recoded symbol by symbol (at most two such halves per channel)
+    if (__any_sync(FULL, (any_hi & 0x80808080u) != 0)) {   // rare: a count >= 128 somewhere in the tile
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int p0 = ts + lane * 64 + h * 32;
+        for (int k = 0; k < NP; ++k) qv[k] = clamp127(qv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) encode16(qv[k], lut4_saddr, satk, satv, pc[k], pl[k]);
+#pragma unroll
+    for (int lev = 1; lev < NP; lev <<= 1) {
+        const bool r = rot & lev;
+        uint32_t tc[NP], tl4[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { tc[j] = r ? pc[(j - lev) & (NP - 1)] : pc[j]; tl4[j] = r ? pl[(j - lev) & (NP - 1)] : pl[j]; }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { pc[j] = tc[j]; pl[j] = tl4[j]; }
+    }
+    unsigned long long acc[NG];
+    uint32_t nb[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        acc[g] = ((unsigned long long)pc[2 * g] << pl[2 * g + 1]) | pc[2 * g + 1];
+        nb[g] = pl[2 * g] + pl[2 * g + 1];                          // 32..64 bits
+    }
+    if (!FULLT) {
+        // head/tail tile: a group outside the window emits nothing; a group cut by the window boundary is
+        // recoded symbol by symbol (at most two such groups per channel)
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int p0 = ts + lane * (32 * NG) + g * 32;
             const int vlo = max(start - p0, 0), vhi = min(end - p0, 32);
             if (vlo > 0 || vhi < 32) {
-                unsigned long long acc = 0;
-                uint32_t nb = 0;
+                unsigned long long ac = 0;
+                uint32_t n1 = 0;
                 for (int i = vlo; i < vhi; ++i) {
-                    const uint32_t e1 = s_lut1[min((uint32_t)tile[h * 32 + i], 15u)];
-                    acc = (acc << (e1 >> 16)) | (e1 & 0xFFFFu);
-                    nb += e1 >> 16;
+                    const uint32_t e1 = s_lut1[min((uint32_t)tile[g * 32 + i], 15u)];
+                    ac = (ac << (e1 >> 16)) | (e1 & 0xFFFFu);
+                    n1 += e1 >> 16;
                 }
-                if (h == 0) { acc0 = acc; nb0 = nb; } else { acc1 = acc; nb1 = nb; }
+                acc[g] = ac;
+                nb[g] = n1;
             }
         }
     }
     // ---- bit offsets ----
-    const uint32_t nb = nb0 + nb1;
-    const uint32_t incl = warp_incl_scan_p(nb);
+    uint32_t nbt = 0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) nbt += nb[g];
+    const uint32_t incl = warp_incl_scan_p(nbt);
     const uint32_t Pnew = Pbits + __shfl_sync(FULL, incl, 31);
-    const uint32_t a = Pbits + incl - nb;
+    const uint32_t a = Pbits + incl - nbt;
     a_lane = a;
-    const uint32_t Wi = a >> 5;
-    // ---- place the two halves back to back: A at bit a, B at bit a + nb0 ----
-    const uint32_t sh0 = a & 31;
-    if (!FULLT) { acc0 = nb0 ? acc0 << (64 - nb0) : 0ull; acc1 = nb1 ? acc1 << (64 - nb1) : 0ull; }
-    else { acc0 <<= (64 - nb0); acc1 <<= (64 - nb1); }
-    const uint32_t Ahi = (uint32_t)(acc0 >> 32), Alo = (uint32_t)acc0;
-    uint32_t A0 = Ahi >> sh0;
-    const uint32_t A1 = __funnelshift_r(Alo, Ahi, sh0);
-    const uint32_t A2 = __funnelshift_r(0u, Alo, sh0);
-    const uint32_t e0 = sh0 + nb0;
-    const uint32_t nf0 = e0 >> 5;                                 // complete words of A: 0..2 (FULLT: 1..2)
-    const uint32_t sh1 = e0 & 31;
-    const uint32_t Bhi = (uint32_t)(acc1 >> 32), Blo = (uint32_t)acc1;
-    uint32_t B0 = Bhi >> sh1;
-    const uint32_t B1 = __funnelshift_r(Blo, Bhi, sh1);
-    const uint32_t B2 = __funnelshift_r(0u, Blo, sh1);
-    const uint32_t e1 = sh1 + nb1;
-    const uint32_t nf1 = e1 >> 5;                                 // complete words of B: 0..2 (FULLT: 1..2)
+    // ---- place the groups back to back; the lane's first complete word waits for the previous lane's partial word ----
+    uint32_t pos = a, cur = 0, firstW = 0, firstIdx = a >> 5;
+    bool have_first = false;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const uint32_t sh = pos & 31, wi = pos >> 5;
+        const unsigned long long A = FULLT ? (acc[g] << (64 - nb[g])) : (nb[g] ? acc[g] << (64 - nb[g]) : 0ull);
+        const uint32_t Ahi = (uint32_t)(A >> 32), Alo = (uint32_t)A;
+        const uint32_t W0 = (Ahi >> sh) | cur;
+        const uint32_t W1 = __funnelshift_r(Alo, Ahi, sh);
+        const uint32_t W2 = __funnelshift_r(0u, Alo, sh);
+        const uint32_t e = sh + nb[g];
+        const uint32_t nf = e >> 5;                               // complete words: 0..2 (FULLT: 1..2)
+        if (FULLT) {
+            if (g == 0) firstW = W0; else s_ring[wi & RM] = W0;
+            if (nf == 2) s_ring[(wi + 1) & RM] = W1;
+            cur = (e & 31) ? (nf == 1 ? W1 : W2) : 0u;
+        } else {
+            if (nf >= 1) {
+                if (!have_first) { firstW = W0; firstIdx = wi; have_first = true; }
+                else s_ring[wi & RM] = W0;
+            }
+            if (nf == 2) s_ring[(wi + 1) & RM] = W1;
+            cur = (e & 31) ? (nf == 0 ? W0 : (nf == 1 ? W1 : W2)) : 0u;
+        }
+        pos += nb[g];
+    }
     if (FULLT) {
-        B0 |= sh1 ? (nf0 == 1 ? A1 : A2) : 0u;                    // A's trailing partial word shares B's first word
-        const uint32_t tl = (e1 & 31) ? (nf1 == 1 ? B1 : B2) : 0u;
-        uint32_t incoming = __shfl_up_sync(FULL, tl, 1);
+        uint32_t incoming = __shfl_up_sync(FULL, cur, 1);
         if (lane == 0) incoming = carry;
-        carry = __shfl_sync(FULL, tl, 31);
-        A0 |= incoming;
-        s_ring[Wi & RM] = A0;
-        if (nf0 == 2) s_ring[(Wi + 1) & RM] = A1;
-        s_ring[(Wi + nf0) & RM] = B0;
-        if (nf1 == 2) s_ring[(Wi + nf0 + 1) & RM] = B1;
+        carry = __shfl_sync(FULL, cur, 31);
+        s_ring[firstIdx & RM] = firstW | incoming;
     } else {
-        B0 |= sh1 ? (nf0 == 0 ? A0 : (nf0 == 1 ? A1 : A2)) : 0u;
-        const uint32_t tl = (e1 & 31) ? (nf1 == 0 ? B0 : (nf1 == 1 ? B1 : B2)) : 0u;
-        const uint32_t incoming = tails_segmented(tl, (nf0 + nf1) > 0, carry, lane);
-        if (nf0 >= 1) A0 |= incoming; else B0 |= incoming;        // the word at Wi
-        if (nf0 >= 1) s_ring[Wi & RM] = A0;
-        if (nf0 == 2) s_ring[(Wi + 1) & RM] = A1;
-        if (nf1 >= 1) s_ring[(Wi + nf0) & RM] = B0;
-        if (nf1 == 2) s_ring[(Wi + nf0 + 1) & RM] = B1;
+        const uint32_t incoming = tails_segmented(cur, have_first, carry, lane);
+        if (have_first) s_ring[firstIdx & RM] = firstW | incoming;
     }
     Pbits = Pnew;
 }
 
-__global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_constant__ EncParams P) {
+__global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fast(const __grid_constant__ EncParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = EncFastSmem;
     constexpr uint32_t RM = SM::RW - 1;
@@ -250,7 +288,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_
 
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, S = T->S;
-    if (S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || T->enc4_off == 0 || (lut4_saddr & 511u)) {
+    if (S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || T->enc4_off == 0 || (lut4_saddr & 255u)) {
         if (threadIdx.x == 0) *P.overflow = 2;   // launch configuration does not match the table block
         return;
     }
@@ -266,7 +304,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_
     const uint32_t satv = (uint32_t)(S - 1) * 0x01010101u;
     const uint32_t slot_units = (uint32_t)min((long long)(P.slot_bytes >> 4), 0x7FFFFFFFll);
 
-    const int gwarp = blockIdx.x * ENC_WARPS + warp, nwarps = gridDim.x * ENC_WARPS;
+    const int gwarp = blockIdx.x * EF_WARPS + warp, nwarps = gridDim.x * EF_WARPS;
     uint32_t slot = 0, parity = 0;   // ring position of the next tile to consume
     int cur_combo = -1;
 
@@ -288,7 +326,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_
             const int A0 = start & ~(ETILE - 1);
             const int nt = (end - A0 + ETILE - 1) / ETILE;
             const int rd_end = (end + 15) & ~15;
-            // chunk (1024-symbol) side info: tile t holds chunks 2t+dj and 2t+dj+1, numbered from start/1024
+            // chunk (1024-symbol) side info: tile t holds chunks EF_NG*t+dj .. +EF_NG-1, numbered from start/1024
             uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride + (A0 / TILE - start / TILE);
             uint8_t* out = P.stream + (size_t)c * P.slot_bytes;
             uint32_t carry = 0;
@@ -308,16 +346,17 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) k_encode_fast(const __grid_
             int ts = A0;
             for (int t = 0; t < nt; ++t, ts += ETILE) {
                 mbar_wait(&s_bar[slot], parity);
-                const uint8_t* tile = s_in + slot * ETILE + lane * 64;
+                const uint8_t* tile = s_in + slot * ETILE + lane * (32 * EF_NG);
                 const uint32_t Pold = Pbits;
                 uint32_t a_lane;
                 const bool full = (ts >= start) && (ts + ETILE <= end);       // warp-uniform
-                if (full) enc_fast_tile<true, RM>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
-                else enc_fast_tile<false, RM>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
-                // chunk offsets: lane 0 starts the tile's first chunk, lane 16 its second
-                if ((lane & 15) == 0) {
-                    const int cs = ts + (lane >> 4) * TILE;                   // absolute start of that chunk
-                    if (cs + TILE > start && cs < end) co[2 * t + (lane >> 4)] = a_lane;
+                if (full) enc_fast_tile<true, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
+                else enc_fast_tile<false, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
+                // chunk offsets: every (32 / EF_NG)-th lane starts one of the tile's EF_NG chunks
+                if ((lane & (32 / EF_NG - 1)) == 0) {
+                    const int k = lane / (32 / EF_NG);
+                    const int cs = ts + k * TILE;                             // absolute start of that chunk
+                    if (cs + TILE > start && cs < end) co[EF_NG * t + k] = a_lane;
                 }
                 // ---- flush complete 128-bit units; refill the TMA slot ----
                 __syncwarp();
