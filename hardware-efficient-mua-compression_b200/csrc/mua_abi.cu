@@ -308,14 +308,21 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
     P.total_bits = d_total_bits; P.overflow = d_overflow;
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
-    if (h.Lmax <= 2) {
+    if (h.Lmax <= 2 && S <= 4) {
         const int smem = EncFastSmem::PER_WARP * EF_WARPS;
-        cudaError_t e = cudaFuncSetAttribute(k_encode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");
         const int per_sm = EF_NG == 2 ? 4 : 5;
         const int need = (C + EF_WARPS - 1) / EF_WARPS;
         const int grid = need < sm_count() * per_sm ? need : sm_count() * per_sm;
-        k_encode_fast<<<grid, EF_WARPS * 32, smem, st>>>(P);
+#define MUA_LAUNCH_ENC(SV)                                                                                          \
+    do {                                                                                                            \
+        cudaError_t e = cudaFuncSetAttribute(k_encode_fast<SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                        \
+        k_encode_fast<SV><<<grid, EF_WARPS * 32, smem, st>>>(P);                                                    \
+    } while (0)
+        if (S == 2) MUA_LAUNCH_ENC(2);
+        else if (S == 3) MUA_LAUNCH_ENC(3);
+        else MUA_LAUNCH_ENC(4);
+#undef MUA_LAUNCH_ENC
     } else {
         const int smem = EncGenSmem::PER_WARP * ENC_WARPS;
         cudaError_t e = cudaFuncSetAttribute(k_encode_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -39,12 +39,14 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
         uint32_t l1 = s_len[r1];
         enc2[tid] = (((uint32_t)s_code[r0] << l1) | s_code[r1]) | (((uint32_t)s_len[r0] + l1) << 24);
     }
-    if (T->enc4_off) {   // Lmax <= 2: four 2-bit symbols per entry
+    if (T->enc4_off && tid < S * S * S * S) {   // Lmax <= 2 (S <= 4): four saturated symbols per entry, index in base S
         uint8_t* enc4 = blob + T->enc4_off + (size_t)(p * K + k) * 512;   // [0,256): codes, [256,512): lengths
         uint32_t code = 0, len = 0;
+        int rest = tid;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int r = s_rank[(tid >> (2 * i)) & 3];   // s_rank saturates values >= S
+            const int r = s_rank[rest % S];
+            rest /= S;
             code = (code << s_len[r]) | s_code[r];
             len += s_len[r];
         }

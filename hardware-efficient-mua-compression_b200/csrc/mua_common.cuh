@@ -13,7 +13,8 @@ constexpr int TILE = MUA_CHUNK;        // symbols per warp tile == decode chunk
 // ---- device table block (built by k_build_tables) ------------------------------------------
 // enc1 : uint32 [S][K][16]    raw nibble b -> (len << 16 | code) of rank[p][min(b,S-1)]
 // enc2 : uint32 [S][K][256]   raw nibble pair (b0 | b1<<4), b0 first in time -> code | len << 24   (general encoder)
-// enc4 : uint8  [S][K][2][256] four saturated 2-bit symbols (q0 | q1<<2 | q2<<4 | q3<<6), q0 first in time
+// enc4 : uint8  [S][K][2][256] four saturated symbols, index in base S (q0 + S*q1 + S^2*q2 + S^3*q3, q0 first in
+//                             time; S^4 <= 256 entries: 81 B for S=3 = one word per bank, conflict-free)
 //                             -> [0][i] = code (<= 8 bits), [1][i] = length; only when Lmax <= 2 (fast encoder)
 // dec  : uint32 [S][K][1<<W]  W = nsym*Lmax bit window -> nsym symbols, one per byte (first symbol in
 //                             byte 0, values < 16) | used_bits << 28

@@ -137,11 +137,12 @@ __device__ __forceinline__ uint32_t lds_u8_256(uint32_t saddr) {   // same index
 //   g   = w + satk            (FMA pipe)  bit 7 of a byte set  <=>  byte > S-1   (bytes < 129: checked per tile)
 //   m   = prmt.msb(g)         (ALU)       0xFF in those bytes
 //   ws  = lop3(w, m, satv)    (ALU)       min(byte, S-1): four 2-bit symbols
-//   p   = ws * 0x01041040     (FMA pipe)  gathers them into the top byte: q0 | q1<<2 | q2<<4 | q3<<6
+//   p   = ws * gmul           (FMA pipe)  gathers them into the top byte in base S: q0 + S*q1 + S^2*q2 + S^3*q3
+//                                         (gmul = S^3 | S^2<<8 | S<<16 | 1<<24; no carries: every partial sum < 256)
 //   adr = prmt(p, lut)        (ALU)       LUT base (256-byte aligned) with its low byte replaced by the index
 //   code = lut[adr], len = lut[adr + 256] (two byte loads: no unpacking)
-__device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uint32_t satk, uint32_t satv, uint32_t& code,
-                                         uint32_t& len) {
+__device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uint32_t satk, uint32_t satv, uint32_t gmul,
+                                         uint32_t& code, uint32_t& len) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t qc[4], ql[4];
 #pragma unroll
@@ -149,7 +150,7 @@ __device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uin
         const uint32_t g = w[j] + satk;
         const uint32_t m = byte_msb_mask(g);
         const uint32_t ws = (w[j] & ~m) | (satv & m);
-        const uint32_t adr = __byte_perm(ws * 0x01041040u, lut4_saddr, 0x7653);
+        const uint32_t adr = __byte_perm(ws * gmul, lut4_saddr, 0x7653);
         qc[j] = lds_u8(adr);
         ql[j] = lds_u8_256(adr);
     }
@@ -173,7 +174,7 @@ __device__ __forceinline__ uint4 clamp127(uint4 q) {
 // index: conflict-free) and a log2(2NG)-level select network puts the results back in order.
 template <bool FULLT, uint32_t RM, int NG>
 __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4_saddr, const uint32_t* s_lut1, uint32_t satk,
-                                              uint32_t satv, int ts, int start, int end, int lane, uint32_t* s_ring,
+                                              uint32_t satv, uint32_t gmul, int ts, int start, int end, int lane, uint32_t* s_ring,
                                               uint32_t& Pbits, uint32_t& carry, uint32_t& a_lane) {
     constexpr int NP = 2 * NG;
     const uint32_t rot = NG == 2 ? ((lane >> 1) & 3) : (lane & 7);
@@ -190,7 +191,7 @@ __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4
         for (int k = 0; k < NP; ++k) qv[k] = clamp127(qv[k]);
     }
 #pragma unroll
-    for (int k = 0; k < NP; ++k) encode16(qv[k], lut4_saddr, satk, satv, pc[k], pl[k]);
+    for (int k = 0; k < NP; ++k) encode16(qv[k], lut4_saddr, satk, satv, gmul, pc[k], pl[k]);
 #pragma unroll
     for (int lev = 1; lev < NP; lev <<= 1) {
         const bool r = rot & lev;
@@ -274,6 +275,7 @@ __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4
     Pbits = Pnew;
 }
 
+template <int SV>   // alphabet size as a compile-time constant: the SWAR constants and the gather multiplier become immediates
 __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fast(const __grid_constant__ EncParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = EncFastSmem;
@@ -287,8 +289,9 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm + SM::BARS);
 
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
-    const int K = T->K, S = T->S;
-    if (S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || T->enc4_off == 0 || (lut4_saddr & 255u)) {
+    const int K = T->K;
+    constexpr int S = SV;
+    if (T->S != SV || S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || S > 4 || T->enc4_off == 0 || (lut4_saddr & 255u)) {
         if (threadIdx.x == 0) *P.overflow = 2;   // launch configuration does not match the table block
         return;
     }
@@ -300,8 +303,9 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
     __syncwarp();
     const uint32_t* g_enc1 = reinterpret_cast<const uint32_t*>(P.tab + T->enc1_off);
     const uint4* g_enc4 = reinterpret_cast<const uint4*>(P.tab + T->enc4_off);
-    const uint32_t satk = (uint32_t)(0x7F - (S - 1)) * 0x01010101u;   // SWAR saturation constants
-    const uint32_t satv = (uint32_t)(S - 1) * 0x01010101u;
+    constexpr uint32_t satk = (uint32_t)(0x7F - (S - 1)) * 0x01010101u;   // SWAR saturation constants
+    constexpr uint32_t satv = (uint32_t)(S - 1) * 0x01010101u;
+    constexpr uint32_t gmul = (uint32_t)(S * S * S) | ((uint32_t)(S * S) << 8) | ((uint32_t)S << 16) | (1u << 24);
     const uint32_t slot_units = (uint32_t)min((long long)(P.slot_bytes >> 4), 0x7FFFFFFFll);
 
     const int gwarp = blockIdx.x * EF_WARPS + warp, nwarps = gridDim.x * EF_WARPS;
@@ -350,8 +354,8 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
                 const uint32_t Pold = Pbits;
                 uint32_t a_lane;
                 const bool full = (ts >= start) && (ts + ETILE <= end);       // warp-uniform
-                if (full) enc_fast_tile<true, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
-                else enc_fast_tile<false, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
+                if (full) enc_fast_tile<true, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, gmul, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
+                else enc_fast_tile<false, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, gmul, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
                 // chunk offsets: every (32 / EF_NG)-th lane starts one of the tile's EF_NG chunks
                 if ((lane & (32 / EF_NG - 1)) == 0) {
                     const int k = lane / (32 / EF_NG);
