@@ -360,6 +360,15 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     const bool smem_lut = lut_bytes <= 32 * 1024;
     if (h.nsym == 4 && h.Lmax <= 2) {
         REQUIRE((long long)C * (slot_bytes >> 4) < (1ll << 32), "stream buffer must be < 64 GiB");
+        if (h.S * h.K <= DL_MAX_COMBO && h.W == 8) {   // lane-private LUT banks: one persistent CTA per SM
+            cudaError_t e = cudaFuncSetAttribute(k_decode_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
+            if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+            const long long blocks_needed = (groups + DL_WARPS - 1) / DL_WARPS;
+            const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
+            k_decode_lane<<<grid, DL_WARPS * 32, DL_SMEM, st>>>(P);
+            CHECK_LAUNCH("k_decode");
+            return MUA_OK;
+        }
         const bool fast_smem_lut = smem_lut;
         const int smem = DF_WARPS * DF_PER_WARP + (fast_smem_lut ? lut_bytes : 0);
         const long long blocks_needed = (groups + DF_WARPS - 1) / DF_WARPS;
