@@ -360,12 +360,17 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     const bool smem_lut = lut_bytes <= 32 * 1024;
     if (h.nsym == 4 && h.Lmax <= 2) {
         REQUIRE((long long)C * (slot_bytes >> 4) < (1ll << 32), "stream buffer must be < 64 GiB");
-        if (h.S * h.K <= DL_MAX_COMBO && h.W == 8) {   // lane-private LUT banks: one persistent CTA per SM
-            cudaError_t e = cudaFuncSetAttribute(k_decode_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
+        if (h.K <= DL_MAX_ROWS && h.S <= 8 && h.W == 8) {   // lane-private LUT banks: one persistent CTA per SM
+#ifndef MUA_DL_NC
+#define MUA_DL_NC 1
+#endif
+            constexpr int NC = MUA_DL_NC;
+            cudaError_t e = cudaFuncSetAttribute(k_decode_lane<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
-            const long long blocks_needed = (groups + DL_WARPS - 1) / DL_WARPS;
+            const long long lgroups = ((long long)C * P.item_chunks + 32 * NC - 1) / (32 * NC);
+            const long long blocks_needed = (lgroups + DL_WARPS / NC - 1) / (DL_WARPS / NC);
             const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
-            k_decode_lane<<<grid, DL_WARPS * 32, DL_SMEM, st>>>(P);
+            k_decode_lane<NC><<<grid, DL_WARPS / NC * 32, DL_SMEM, st>>>(P);
             CHECK_LAUNCH("k_decode");
             return MUA_OK;
         }

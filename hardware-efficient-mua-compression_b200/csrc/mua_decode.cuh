@@ -314,14 +314,17 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
     }
 }
 
-// ---- fast decoder with lane-private LUT banks (NSYM = 4, Lmax = 2, S*K <= 3: the chosen system) ----
+// ---- fast decoder with lane-private LUT banks (NSYM = 4, W = 8, K <= 3, S <= 8: the chosen system) ----
 // k_decode_fast is bound by the LSU data pipe, and ~45 % of its shared-memory wavefronts are bank conflicts of
 // the LUT gathers (32 lanes index a 256-word table with skewed, data-dependent indices: ~3.7 wavefronts per
-// lookup).  Here every lane owns a bank: entry i of (peak,row) pair c for lane l lives at byte
-// c*32K + i*128 + l*4, so a lookup is ONE wavefront whatever the 32 indices are.  The replicated tables take
-// 3 * 32 KB, which leaves room for 14 warps per SM only if the per-lane stream staging shrinks (a 128-byte ring
-// instead of the whole chunk).  With 14 warps the
-// kernel is latency bound, so the dependent chain of a lookup and everything around it is kept short:
+// lookup).  Here every lane owns a bank: entry i of codebook row k for lane l lives at byte k*32K + i*128 + l*4,
+// so a lookup is ONE wavefront whatever the 32 indices are.  A replicated table takes 32 KB, so there is one per
+// codebook ROW only: the tables hold RANKS (the table of peak 0, whose rank map is the identity) and the lane's
+// peak is applied by the PRMT that unpacks an entry -- the entry's low 16 bits are four byte selectors into the
+// lane's rank -> symbol map (TabHdr::idx[p], 8 bytes in two registers), which costs the same one instruction as
+// the mask it replaces.  What is left of the SM's shared memory feeds 20 warps (K = 1) only because the per-lane
+// stream staging is a 128-byte ring instead of the whole chunk.  The kernel is latency bound (one dependent
+// chain per lane), so the chain of a lookup and everything around it is kept short:
 //   * the stream is kept bit-reversed in registers (stream bit j at register bit j) and the tables are indexed
 //     by the bit-reversed window, so the window of lookup k lands on address bits [14:7] with ONE funnel shift
 //     by the running bit count; the tables are 32 KB aligned in the shared window so that one LOP3 masks the
@@ -329,12 +332,11 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 //   * the stream reaches each lane through a 128-byte ring that is topped up with cp.async (LDGSTS) one
 //     128-symbol period ahead of its use; the next group's first bytes are requested before the last period of
 //     the current group is written out;
-//   * the per-chunk bookkeeping (window, chunk offset, pointers) is prefetched into L1 one group ahead;
 //   * the write-out (8 lanes per 128-byte row) uses per-group precomputed row pointers and is fully unrolled.
-constexpr int DL_WARPS = 14;
-constexpr int DL_ROW_B = 144;          // staged stream bytes per lane and half chunk
+constexpr int DL_WARPS = 14;           // launched warps (more do not help: see profiles/r01_summary.md); those with a buffer in the runtime layout work
+constexpr int DL_ROW_B = 144;          // stream ring row: 128 B + 16 B pad
 constexpr int DL_OUT_B = 144;          // output tile row: 128 B + 16 B pad
-constexpr int DL_MAX_COMBO = 3;
+constexpr int DL_MAX_ROWS = 3;         // codebook rows (K) whose lane-replicated tables fit
 constexpr int DL_TAB_B = 256 * 32 * 4; // one lane-replicated table: 32 KB
 constexpr int DL_PER_WARP = 32 * DL_ROW_B + 32 * DL_OUT_B;
 constexpr int DL_SMEM = 227 * 1024;    // everything the SM has: tables sit at 32 KB aligned addresses, warps around them
@@ -350,7 +352,7 @@ struct DecItem {
     uint32_t bp;             // bit position of the chunk in the channel's stream
     const uint8_t* sbase;    // the channel's slot
     uint8_t* optr;           // where the chunk's first symbol goes
-    int combo;               // (peak, codebook row) pair
+    int pk, en;              // peak (rank -> symbol map) and codebook row (table)
 };
 
 // volatile loads: issued where they are written (the compiler would otherwise sink them to their first use)
@@ -358,22 +360,6 @@ __device__ __forceinline__ int ldg_s32(const int32_t* p) { int v; asm volatile("
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 __device__ __forceinline__ int ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (int)v; }
 __device__ __forceinline__ long long ldg_s64(const int64_t* p) { long long v; asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
-
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// the bookkeeping of one lane's chunk is prefetched into L1 one group ahead (dec_prefetch) and loaded right
-// before it is needed (dec_load): prefetches have no results, so nothing can be scheduled to wait on them early
-__device__ __forceinline__ void dec_prefetch(const DecParams& P, long long item, long long nitems) {
-    if (item < nitems) {
-        const int c = (int)(item / P.item_chunks), j = (int)(item - (long long)c * P.item_chunks);
-        prefetch_l1(P.start + c);
-        prefetch_l1(P.end + c);
-        prefetch_l1(P.peak + c);
-        prefetch_l1(P.enc + c);
-        prefetch_l1(P.chunk_off + (size_t)c * P.chunk_stride + j);
-        if (P.off) prefetch_l1(P.off + c);
-    }
-}
 
 __device__ __forceinline__ DecRaw dec_load(const DecParams& P, long long item, long long nitems) {
     DecRaw r;
@@ -394,7 +380,7 @@ __device__ __forceinline__ DecItem dec_finish(const DecParams& P, DecRaw r, int 
     // nothing derived from the loaded values may be scheduled before this point
     asm volatile("" : "+r"(r.start), "+r"(r.end), "+r"(r.pk), "+r"(r.en), "+r"(r.bp), "+l"(r.off));
     DecItem it;
-    it.rem = 0; it.bp = 0; it.sbase = P.stream; it.optr = P.dec; it.combo = 0;
+    it.rem = 0; it.bp = 0; it.sbase = P.stream; it.optr = P.dec; it.pk = 0; it.en = 0;
     if (r.valid && r.end > r.start && r.start >= 0) {
         const int j0 = r.start / TILE;
         const int nch = (r.end + TILE - 1) / TILE - j0;
@@ -404,22 +390,13 @@ __device__ __forceinline__ DecItem dec_finish(const DecParams& P, DecRaw r, int 
             it.bp = r.bp;
             it.sbase = P.stream + (size_t)r.c * P.slot_bytes;
             it.optr = P.dec + r.off + a;
-            it.combo = r.pk * K + r.en;
+            it.pk = r.pk;
+            it.en = r.en;
         }
     }
     return it;
 }
 
-#ifdef MUA_PF_LOAD
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    uint32_t d;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(d) : "l"(reinterpret_cast<const void*>(reinterpret_cast<unsigned long long>(p) & ~3ull)));
-}
-#elif defined(MUA_PF_NONE)
-__device__ __forceinline__ void prefetch_l2(const void* p) {}
-#else
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#endif
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
@@ -441,143 +418,202 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, unsigned long long src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(DL_WARPS * 32, 1) k_decode_lane(const __grid_constant__ DecParams P) {
+// NC = chunks decoded concurrently by one lane (independent dependency chains interleaved in one instruction
+// stream).  The shared-memory budget fixes the number of chains per SM (14 * 32), so NC = 2 runs 7 warps.
+template <int NC>
+__global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(128) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K;
-    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->W != 8 || T->S * K > DL_MAX_COMBO) return;
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->W != 8 || K > DL_MAX_ROWS || T->S > 8) return;
     const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- shared-memory layout: tables at the first 32 KB boundary, per-warp buffers below and above them ----
-    const uint32_t base_a = smem_u32(dsm);
+    // ---- shared-memory layout: rank -> symbol maps, then per-(warp, chain) buffers below and above the tables,
+    //      which sit at the first 32 KB boundary ----
+    const uint32_t map_a = smem_u32(dsm);                         // uint2 [8]: idx[p][0..7]
+    const uint32_t base_a = map_a + 128;
     const uint32_t tab_a = (base_a + (DL_TAB_B - 1)) & ~(uint32_t)(DL_TAB_B - 1);
-    const uint32_t hi_a = tab_a + DL_MAX_COMBO * DL_TAB_B;
+    const uint32_t hi_a = tab_a + K * DL_TAB_B;
+    const uint32_t end_a = map_a + DL_SMEM;
     const int n_low = (int)((tab_a - base_a) / DL_PER_WARP);
-    const int n_high = hi_a <= base_a + DL_SMEM ? (int)((base_a + DL_SMEM - hi_a) / DL_PER_WARP) : 0;
-    const int nw = min(DL_WARPS, n_low + n_high);                 // warps that have a buffer (14 with the usual window base)
+    const int n_high = hi_a <= end_a ? (int)((end_a - hi_a) / DL_PER_WARP) : 0;
+    const int nw = min(DL_WARPS, n_low + n_high) / NC;            // warps that have their buffers
     {
-        uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm + (tab_a - base_a));
-        const int nword = (T->S * K) * 256 * 32;
+        // table of row k = the dec table of (peak 0, row k), whose symbols are the ranks; entry = four rank nibbles
+        // (PRMT byte selectors) in the low 16 bits | used bits << 28; indexed by the bit-reversed window
+        uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm + (tab_a - map_a));
+        const int nword = K * 256 * 32;
         for (int i = threadIdx.x; i < nword; i += blockDim.x) {
-            const int e = i >> 5, c = e >> 8, idx = e & 255;
-            s_lut[(c * 256 + (int)(__brev((uint32_t)idx) >> 24)) * 32 + (i & 31)] = g_lut[e];
+            const int e = i >> 5, k = e >> 8, idx = e & 255;
+            const uint32_t v = g_lut[k * 256 + idx];
+            const uint32_t sel = (v & 0xFu) | ((v >> 4) & 0xF0u) | ((v >> 8) & 0xF00u) | ((v >> 12) & 0xF000u);
+            s_lut[(k * 256 + (int)(__brev((uint32_t)idx) >> 24)) * 32 + (i & 31)] = sel | (v & 0xF0000000u);
+        }
+        if (threadIdx.x < 16) {
+            const int p = threadIdx.x >> 1, h = threadIdx.x & 1;
+            uint32_t m = 0;
+            if (p < T->S)
+                for (int r = 0; r < 4; ++r) m |= (uint32_t)T->idx[p][4 * h + r] << (8 * r);
+            reinterpret_cast<uint32_t*>(dsm)[threadIdx.x] = m;
         }
     }
     __syncthreads();
     if (warp >= nw) return;
-    const uint32_t buf_a = warp < n_low ? base_a + warp * DL_PER_WARP : hi_a + (warp - n_low) * DL_PER_WARP;
-    uint8_t* s_str = dsm + (buf_a - base_a);
-    uint8_t* s_out = s_str + 32 * DL_ROW_B;
+    uint32_t buf_a[NC], ring_a[NC];
+    const uint32_t* rowp[NC];
+    uint8_t* s_out[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int u = warp * NC + c;
+        buf_a[c] = u < n_low ? base_a + u * DL_PER_WARP : hi_a + (u - n_low) * DL_PER_WARP;
+        uint8_t* s_str = dsm + (buf_a[c] - map_a);
+        s_out[c] = s_str + 32 * DL_ROW_B;
+        rowp[c] = reinterpret_cast<const uint32_t*>(s_str + lane * DL_ROW_B);
+        ring_a[c] = buf_a[c] + lane * DL_ROW_B;
+    }
     const long long nitems = (long long)P.C * P.item_chunks;
-    const long long ngroups = (nitems + 31) / 32;
+    const long long ngroups = (nitems + 32 * NC - 1) / (32 * NC);
     const int wrow = lane >> 3, wcol = lane & 7;
-    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(s_str + lane * DL_ROW_B);
-    const uint32_t ring_a = buf_a + lane * DL_ROW_B;
     const unsigned long long lo_addr = reinterpret_cast<unsigned long long>(P.stream);
     const unsigned long long hi_addr = lo_addr + (unsigned long long)P.C * (unsigned long long)P.slot_bytes;
 
     // first 96 bytes of a chunk (>= 65 bytes past its first bit); pieces outside the stream buffer are skipped
-    auto ring_start = [&](const DecItem& it, DecRing& R) {
+    auto ring_start = [&](const DecItem& it, DecRing& R, uint32_t ra) {
         R.org = (reinterpret_cast<unsigned long long>(it.sbase) + (it.bp >> 3)) & ~31ull;
         R.wp = 96;
         if (it.rem > 0) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const unsigned long long a = R.org + 16 * k;
-                if (a >= lo_addr && a + 16 <= hi_addr) cp_async16(ring_a + 16 * k, a);
+                if (a >= lo_addr && a + 16 <= hi_addr) cp_async16(ra + 16 * k, a);
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     const long long gstride = (long long)gridDim.x * nw;
     long long g = (long long)blockIdx.x * nw + warp;
-    DecItem cur = dec_finish(P, dec_load(P, g * 32 + lane, g < ngroups ? nitems : 0), K);
-    DecRing R;
-    ring_start(cur, R);
+    DecItem cur[NC];
+    DecRing R[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        cur[c] = dec_finish(P, dec_load(P, (g * NC + c) * 32 + lane, g < ngroups ? nitems : 0), K);
+        ring_start(cur[c], R[c], ring_a[c]);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     while (g < ngroups) {
         const long long gn = g + gstride;
-        dec_prefetch(P, gn * 32 + lane, gn < ngroups ? nitems : 0);                   // loaded when this group is done
-        const uint32_t lbase = tab_a + (uint32_t)cur.combo * DL_TAB_B + lane * 4;     // this lane's bank of its table
-        const int rem = cur.rem;
-        // write-out roles: in pass i this lane stores 16 bytes of row 4i + wrow
-        unsigned long long wptr[8];
-        int wrem[8];
-        uint32_t wal = 0;
+        const long long nlim = gn < ngroups ? nitems : 0;
+        uint32_t lbase[NC], mlo[NC], mhi[NC], rp[NC], off[NC], w0[NC], w1[NC], wn[NC];
+        int rem[NC];
+        // write-out roles: in pass i this lane stores 16 bytes of row 4i + wrow of every chain's tile
+        unsigned long long wptr[NC][8];
+        uint32_t wrem[NC][4];                                                         // valid bytes from this lane's column on, + 128, two per register
+        uint32_t wal[NC];
+        int maxrem = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + wrow;
-            wptr[i] = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(cur.optr), r) + wcol * 16;
-            wrem[i] = __shfl_sync(FULL, rem, r) - wcol * 16;
-            wal |= ((wptr[i] & 15) == 0 ? 1u : 0u) << i;
+        for (int c = 0; c < NC; ++c) {
+            lbase[c] = tab_a + (uint32_t)cur[c].en * DL_TAB_B + lane * 4;             // this lane's bank of its row's table
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mlo[c]), "=r"(mhi[c]) : "r"(map_a + cur[c].pk * 8));
+            rem[c] = cur[c].rem;
+            maxrem = max(maxrem, rem[c]);
+            wal[c] = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + wrow;
+                wptr[c][i] = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(cur[c].optr), r) + wcol * 16;
+                const uint32_t wr = (uint32_t)(__shfl_sync(FULL, rem[c], r) - wcol * 16 + 128);
+                wrem[c][i >> 1] = (i & 1) ? (wrem[c][i >> 1] | (wr << 16)) : wr;
+                wal[c] |= ((wptr[c][i] & 15) == 0 ? 1u : 0u) << i;
+            }
+            // position of the chunk's first bit in the ring frame
+            const uint32_t boff =
+                (uint32_t)(reinterpret_cast<unsigned long long>(cur[c].sbase) + (cur[c].bp >> 3) - R[c].org) * 8 + (cur[c].bp & 7);
+            rp[c] = boff >> 5;
+            off[c] = boff & 31;
+            w0[c] = w1[c] = wn[c] = 0;
         }
-        // position of the chunk's first bit in the ring frame
-        const uint32_t boff = (uint32_t)(reinterpret_cast<unsigned long long>(cur.sbase) + (cur.bp >> 3) - R.org) * 8 + (cur.bp & 7);
-        uint32_t rp = boff >> 5, off = boff & 31;
-        uint32_t w0 = 0, w1 = 0, wn = 0;
         int done = 0;
-        const int nper = max((__reduce_max_sync(FULL, rem) + 127) >> 7, 1);           // periods of this group
-        DecRaw nraw;
+        const int nper = max((__reduce_max_sync(FULL, maxrem) + 127) >> 7, 1);        // periods of this group
         for (int per = 0; per < nper; ++per) {
-            if (per == max(nper - 2, 0)) nraw = dec_load(P, gn * 32 + lane, gn < ngroups ? nitems : 0);   // one period before use
-            // ---- top the ring up for the NEXT period, then wait for everything issued before that ----
-            if (rem > done + 128) {
-                const uint32_t rd32 = (done == 0 ? rp : rp - 3) * 4 & ~31u;          // read position, rounded down to 32 bytes
-                if (R.wp + 32 - rd32 <= 128) {
+            // ---- top the rings up for the NEXT period, then wait for everything issued before that ----
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const unsigned long long a = R.org + R.wp + 16 * k;
-                        if (a + 16 <= hi_addr) cp_async16(ring_a + ((R.wp + 16 * k) & 127), a);
+            for (int c = 0; c < NC; ++c) {
+                if (rem[c] > done + 128) {
+                    const uint32_t rd32 = (done == 0 ? rp[c] : rp[c] - 3) * 4 & ~31u;  // read position, rounded down to 32 bytes
+                    if (R[c].wp + 32 - rd32 <= 128) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const unsigned long long a = R[c].org + R[c].wp + 16 * k;
+                            if (a + 16 <= hi_addr) cp_async16(ring_a[c] + ((R[c].wp + 16 * k) & 127), a);
+                        }
+                        R[c].wp += 32;
                     }
-                    R.wp += 32;
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             if (done == 0) {
-                w0 = stream_rev(rowp[rp]); w1 = stream_rev(rowp[rp + 1]); wn = stream_rev(rowp[rp + 2]);
-                rp += 3;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    w0[c] = stream_rev(rowp[c][rp[c]]); w1[c] = stream_rev(rowp[c][rp[c] + 1]); wn[c] = stream_rev(rowp[c][rp[c] + 2]);
+                    rp[c] += 3;
+                }
             }
-            // ---- 128 symbols per lane into the output tile ----
-            uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DL_OUT_B);
+            // ---- 128 symbols per lane and chain into the output tiles ----
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                uint32_t ow[4];
-                const uint32_t xr = __funnelshift_r(w0, w1, off);    // next 32 stream bits, first one at bit 0
-                const uint32_t xl = xr << 7, xh = xr >> 25;
-                uint32_t o = 0;
+                uint32_t ow[NC][4], xl[NC], xh[NC], o[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const uint32_t xr = __funnelshift_r(w0[c], w1[c], off[c]);       // next 32 stream bits, first one at bit 0
+                    xl[c] = xr << 7; xh[c] = xr >> 25;
+                    o[c] = 0;
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t t = __funnelshift_r(xl, xh, o);   // window of this lookup on bits [14:7]
-                    uint32_t adr;                                        // (t & 0x7F80) | lbase in one LOP3
-                    asm("lop3.b32 %0, %1, 0x7F80, %2, 0xEA;" : "=r"(adr) : "r"(t), "r"(lbase));
-                    const uint32_t e = lds_u32(adr);
-                    ow[k] = e & 0x0F0F0F0Fu;
-                    o += e >> 28;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const uint32_t t = __funnelshift_r(xl[c], xh[c], o[c]);      // window of this lookup on bits [14:7]
+                        uint32_t adr;                                                    // (t & 0x7F80) | lbase in one LOP3
+                        asm("lop3.b32 %0, %1, 0x7F80, %2, 0xEA;" : "=r"(adr) : "r"(t), "r"(lbase[c]));
+                        const uint32_t e = lds_u32(adr);
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ow[c][k]) : "r"(mlo[c]), "r"(mhi[c]), "r"(e));   // ranks -> symbols
+                        o[c] += e >> 28;
+                    }
                 }
-                off += o;
-                if (off >= 32) { w0 = w1; w1 = wn; wn = stream_rev(rowp[rp & 31]); ++rp; off -= 32; }
-                orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    off[c] += o[c];
+                    if (off[c] >= 32) { w0[c] = w1[c]; w1[c] = wn[c]; wn[c] = stream_rev(rowp[c][rp[c] & 31]); ++rp[c]; off[c] -= 32; }
+                    reinterpret_cast<uint4*>(s_out[c] + lane * DL_OUT_B)[q] = make_uint4(ow[c][0], ow[c][1], ow[c][2], ow[c][3]);
+                }
             }
             if (per == nper - 1) {   // every ring of the warp is free: start the next group's chunks before writing this period out
-                cur = dec_finish(P, nraw, K);
-                ring_start(cur, R);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    cur[c] = dec_finish(P, dec_load(P, (gn * NC + c) * 32 + lane, nlim), K);
+                    ring_start(cur[c], R[c], ring_a[c]);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
             __syncwarp();
             // ---- coalesced write-out: 8 lanes per 128-byte row, 4 rows per pass ----
-            uint4 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(s_out + (i * 4 + wrow) * DL_OUT_B + wcol * 16);
+            for (int c = 0; c < NC; ++c) {
+                uint4 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int vr = wrem[i] - done;                   // valid bytes from this lane's column on
-                uint8_t* d = reinterpret_cast<uint8_t*>(wptr[i]) + done;
-                if (vr >= 16 && ((wal >> i) & 1)) {
-                    *reinterpret_cast<uint4*>(d) = v[i];
-                } else if (vr > 0) {   // window edge or unaligned first chunk: byte stores
-                    const uint8_t* sp = s_out + (i * 4 + wrow) * DL_OUT_B + wcol * 16;
-                    const int nbyte = min(16, vr);
-                    for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(s_out[c] + (i * 4 + wrow) * DL_OUT_B + wcol * 16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int vr = (int)((wrem[c][i >> 1] >> (16 * (i & 1))) & 0xFFFFu) - 128 - done;   // valid bytes from this lane's column on
+                    uint8_t* d = reinterpret_cast<uint8_t*>(wptr[c][i]) + done;
+                    if (vr >= 16 && ((wal[c] >> i) & 1)) {
+                        *reinterpret_cast<uint4*>(d) = v[i];
+                    } else if (vr > 0) {   // window edge or unaligned first chunk: byte stores
+                        const uint8_t* sp = s_out[c] + (i * 4 + wrow) * DL_OUT_B + wcol * 16;
+                        const int nbyte = min(16, vr);
+                        for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                    }
                 }
             }
             __syncwarp();

@@ -165,3 +165,48 @@ def test_dropin_level0_script_loop(recordings):
     got = [float.fromhex(h) for h in json.loads(out.stdout.strip().splitlines()[-1])]
     want = np.load(os.path.join(GOLDEN, "chosen_system.npz"))["BR"]
     assert np.array(got, dtype=np.float64).tobytes() == want[:2].tobytes()
+
+
+@pytest.mark.parametrize("case", ["S3_K3", "S4_K1", "S4_K2"])
+def test_lane_decoder_domain(case):
+    """The lane-private-LUT decoder (k_decode_lane) serves every codebook with 8-bit windows of 4 symbols, up to 3 rows
+    and S <= 8: several rows with different (non-canonical) codewords, every peak (rank maps applied by PRMT), ragged
+    rows, unaligned and empty windows, more chunks than one warp group.  Streams == oracle, decode lossless."""
+    rng = np.random.default_rng(7)
+    if case == "S3_K3":
+        S, lens = 3, np.array([[1, 2, 2], [1, 2, 2], [1, 2, 2]])
+        codes = np.array([[0, 2, 3], [1, 0, 1], [0, 3, 2]])          # '0','10','11' / '1','00','01' / '0','11','10'
+    elif case == "S4_K1":
+        S, lens, codes = 4, np.array([[2, 2, 2, 2]]), np.array([[3, 1, 0, 2]])
+    else:
+        S, lens, codes = 4, np.array([[2, 2, 2, 2], [2, 2, 2, 2]]), np.array([[0, 1, 2, 3], [2, 3, 1, 0]])
+    cb = mua_b200.Codebook(S, lens, codes=codes, device=DEV)
+    # channels whose most frequent symbol differs (all peaks), lengths from 1 to ~40 chunks
+    chans = []
+    for i in range(70):
+        n = int(rng.integers(1, 41000)) if i % 7 else int(rng.integers(1, 300))
+        p = np.full(S, 0.1); p[i % S] = 1.0; p /= p.sum()
+        x = rng.choice(S + 2, size=n, p=np.concatenate([p * 0.97, [0.02, 0.01]])).astype(np.uint8)   # values >= S saturate
+        chans.append(x)
+    rec = P.Recording.from_channels(chans, DEV)
+    lens_n = np.array([len(x) for x in chans])
+    st = np.array([int(rng.integers(0, max(1, n // 3))) for n in lens_n], dtype=np.int32)
+    en = np.array([int(rng.integers(s, n + 1)) for s, n in zip(st, lens_n)], dtype=np.int32)
+    en[5] = st[5]                                                    # empty window
+    en[6] = -1                                                       # skipped channel (window rule)
+    pk = np.array([i % S for i in range(70)], dtype=np.uint8)
+    ec = np.array([i % lens.shape[0] for i in range(70)], dtype=np.uint8)
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    es = P.encode(rec, cb, t(st), t(en), t(pk), t(ec))
+    assert int(es.overflow.item()) == 0
+    dec = P.decode(es, rec, cb, t(st), t(en), t(pk), t(ec))
+    assert int(P.verify(rec, dec, S, t(st), t(en)).item()) == 0
+    for c, x in enumerate(chans):
+        if en[c] <= st[c]:
+            assert int(es.total_bits[c]) == 0
+            continue
+        k = int(ec[c])
+        want, total, offs = O.encode_channel(x, int(st[c]), int(en[c]), S, O.rank_of_symbol(int(pk[c]), S), codes[k], lens[k])
+        assert int(es.total_bits[c]) == total and np.array_equal(es.channel_bytes(c), want)
+        got = rec.channel_to_host(c, dec)[st[c]:en[c]]
+        assert np.array_equal(got, np.minimum(x[st[c]:en[c]], S - 1))
