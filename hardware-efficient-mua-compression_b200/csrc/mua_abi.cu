@@ -72,6 +72,11 @@ void layout_sizes(int S, int K, int Lmax, TabHdr* h) {
         h->enc4_off = next;
         next = align_up(next + S * K * 256 * 2, 512);
     }
+    h->encp_off = 0;
+    if (Lmax <= 8) {
+        h->encp_off = next;
+        next = align_up(next + S * K * 512, 512);
+    }
     h->dec_off = next;
     h->total_bytes = align_up(h->dec_off + ((S * K) << h->W) * 4, 512);
 }
@@ -323,6 +328,25 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         else if (S == 3) MUA_LAUNCH_ENC(3);
         else MUA_LAUNCH_ENC(4);
 #undef MUA_LAUNCH_ENC
+    } else if (h.Lmax <= 8 && S >= 3 && S <= 9) {
+        const int smem = EncPairSmem::PER_WARP * ENC_WARPS;
+        const int grid = ctas_needed < sm_count() * 3 ? ctas_needed : sm_count() * 3;
+#define MUA_LAUNCH_ENCP(SV)                                                                                         \
+    do {                                                                                                            \
+        cudaError_t e = cudaFuncSetAttribute(k_encode_pair<SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                        \
+        k_encode_pair<SV><<<grid, ENC_WARPS * 32, smem, st>>>(P);                                                   \
+    } while (0)
+        switch (S) {
+            case 3: MUA_LAUNCH_ENCP(3); break;
+            case 4: MUA_LAUNCH_ENCP(4); break;
+            case 5: MUA_LAUNCH_ENCP(5); break;
+            case 6: MUA_LAUNCH_ENCP(6); break;
+            case 7: MUA_LAUNCH_ENCP(7); break;
+            case 8: MUA_LAUNCH_ENCP(8); break;
+            default: MUA_LAUNCH_ENCP(9); break;
+        }
+#undef MUA_LAUNCH_ENCP
     } else {
         const int smem = EncGenSmem::PER_WARP * ENC_WARPS;
         cudaError_t e = cudaFuncSetAttribute(k_encode_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -53,6 +53,15 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
         enc4[tid] = (uint8_t)code;
         enc4[256 + tid] = (uint8_t)len;
     }
+    if (T->encp_off && tid < (S + 1) * (S + 1)) {   // Lmax <= 8: symbol pairs, index in base S+1 (digit S = no symbol)
+        uint8_t* encp = blob + T->encp_off + (size_t)(p * K + k) * 512;
+        const int q0 = tid / (S + 1), q1 = tid % (S + 1);
+        uint32_t code = 0, len = 0;
+        if (q0 < S) { const int r = s_rank[q0]; code = s_code[r]; len = s_len[r]; }
+        if (q1 < S) { const int r = s_rank[q1]; code = (code << s_len[r]) | s_code[r]; len += s_len[r]; }
+        reinterpret_cast<uint16_t*>(encp)[tid] = (uint16_t)code;
+        encp[256 + 2 * tid] = (uint8_t)len;
+    }
     const int nsym = T->nsym;
     for (int v = tid; v < (1 << W); v += blockDim.x) {
         uint32_t e = 0;

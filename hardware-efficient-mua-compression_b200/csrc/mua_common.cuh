@@ -16,13 +16,17 @@ constexpr int TILE = MUA_CHUNK;        // symbols per warp tile == decode chunk
 // enc4 : uint8  [S][K][2][256] four saturated symbols, index in base S (q0 + S*q1 + S^2*q2 + S^3*q3, q0 first in
 //                             time; S^4 <= 256 entries: 81 B for S=3 = one word per bank, conflict-free)
 //                             -> [0][i] = code (<= 8 bits), [1][i] = length; only when Lmax <= 2 (fast encoder)
+// encp : [S][K] x 512 B      two saturated symbols (or the null symbol S = "outside the window": no bits), index
+//                             i = q1 + (S+1)*q0 (q0 first in time): uint16 code at byte 2i, uint8 length at byte
+//                             256 + 2i; only when Lmax <= 8 (pair encoder)
 // dec  : uint32 [S][K][1<<W]  W = nsym*Lmax bit window -> nsym symbols, one per byte (first symbol in
 //                             byte 0, values < 16) | used_bits << 28
 struct TabHdr {
     int32_t S, K, Lmax, W;
     int32_t nsym;                    // symbols decoded per LUT lookup (4, 2 or 1)
     int32_t enc1_off, enc2_off, enc4_off, dec_off, total_bytes;
-    int32_t pad[6];
+    int32_t encp_off;                // 0 when Lmax > 8
+    int32_t pad[5];
     uint8_t lens[MUA_MAX_K][16];     // SCLV rows (Stored_SCLVs_S_<S>.pkl), ascending lengths
     uint16_t codes[MUA_MAX_K][16];   // codeword of rank r
     uint8_t rank[MUA_MAX_S][16];     // rank[p][s]: approx_sort permutation for peak p (functions_1.py:75-90)

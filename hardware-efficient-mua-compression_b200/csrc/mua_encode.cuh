@@ -8,6 +8,8 @@
 //                   saturated with 5 SWAR ops per 4 symbols, 4 symbols are gathered into one 8-bit
 //                   index with one multiply and coded with ONE 16-bit LUT read; <= 64 bits per lane
 //                   stay in registers.
+//   k_encode_pair : codebooks with Lmax <= 8 (S <= 9): pair LUT in base S+1 with a null digit for symbols outside
+//                   the window, 8-symbol pieces OR-ed into a zeroed ring with shared-memory atomics.
 //   k_encode_gen  : any codebook (Lmax <= 9): nibble-pair LUT + sequential per-lane bit writer.
 #pragma once
 #include "mua_common.cuh"
@@ -553,6 +555,228 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
                 parity ^= (slot == 0);
             }
             flush_last<RM>(s_ring, out, Pbits, carry, slot_units, P.overflow, lane);
+            __syncwarp();
+        }
+        if (lane == 0) P.total_bits[c] = Pbits;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair encoder (Lmax <= 8: every SCLV table up to S = 9)
+// ---------------------------------------------------------------------------------------------
+// Same tiling as the general encoder (warp per channel, 1024-symbol tiles, lane = 32 consecutive symbols, TMA ring),
+// but the per-symbol work follows the fast encoder:
+//   * bytes are saturated with the carry-free SWAR sequence (add on the FMA pipe, PRMT sign-replicate mask, LOP3);
+//   * one multiply by 2 | 2(S+1) << 8 turns the four symbols of a word into two byte offsets (bytes 1 and 3) of
+//     pair-table entries in base S+1, spliced into the table's shared address by one PRMT each; the pair's code
+//     (uint16) and length (uint8) are two loads from that one address;
+//   * digit S of the base-(S+1) index is a null symbol without bits: symbols outside the window are replaced by
+//     it (SWAR range mask), so head and tail tiles run the same code as full tiles;
+//   * pairs are merged to 8-symbol pieces (<= 64 bits) in registers; a prefix sum of the lanes' bit counts gives the
+//     bit offsets; every piece is OR-ed into a zeroed staging ring with shared-memory atomics -- words that are
+//     all zero (the common codeword of the most frequent symbol is '0') are not touched at all; the flush writes
+//     complete 128-bit units with coalesced 16-byte stores and re-zeroes what it has read.
+struct EncPairSmem {
+    static constexpr int RW = 512;                              // staging ring words: 1024 symbols * 8 bits = 256 words + the open unit
+    static constexpr int IN = 0;                                // ENC_NST * TILE bytes
+    static constexpr int LUTP = IN + ENC_NST * TILE;            // 512 B, 256-byte aligned: codes, then lengths
+    static constexpr int LUT1 = LUTP + 512;
+    static constexpr int RING = LUT1 + 64;
+    static constexpr int BARS = RING + RW * 4;
+    static constexpr int PER_WARP = (BARS + ENC_NST * 8 + 511) / 512 * 512;
+};
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// flush the complete 128-bit units in [Pold, Pnew) and zero them in the ring (<= 32 units per call)
+template <uint32_t RM>
+__device__ __forceinline__ void flush_units_z(uint32_t* s_ring, uint8_t* out, uint32_t Pold, uint32_t Pnew, uint32_t slot_units,
+                                              int32_t* overflow, int lane) {
+    const uint32_t u = (Pold >> 7) + lane;
+    if (u < (Pnew >> 7)) {
+        uint4* rp = reinterpret_cast<uint4*>(&s_ring[(u * 4) & RM]);
+        uint4 v4 = *rp;
+        *rp = make_uint4(0, 0, 0, 0);
+        if (u < slot_units) {
+            v4.x = bswap32(v4.x); v4.y = bswap32(v4.y); v4.z = bswap32(v4.z); v4.w = bswap32(v4.w);
+            *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
+        } else {
+            *overflow = 1;
+        }
+    }
+}
+
+template <int SV, bool FULLT, uint32_t RM>
+__device__ __forceinline__ void enc_pair_tile(const uint8_t* tile, uint32_t lutp_saddr, int ts, int start, int end, int lane,
+                                              uint32_t* s_ring, uint32_t& Pbits) {
+    constexpr uint32_t satk = (uint32_t)(0x7F - (SV - 1)) * 0x01010101u;
+    constexpr uint32_t satv = (uint32_t)(SV - 1) * 0x01010101u;
+    constexpr uint32_t nullv = (uint32_t)SV * 0x01010101u;
+    constexpr uint32_t mult = 2u | ((uint32_t)(2 * (SV + 1)) << 8);
+    uint4 qa = *reinterpret_cast<const uint4*>(tile), qb = *reinterpret_cast<const uint4*>(tile + 16);
+    if (__any_sync(FULL, (((qa.x | qa.y) | (qa.z | qa.w) | (qb.x | qb.y) | (qb.z | qb.w)) & 0x80808080u) != 0)) {
+        qa = clamp127(qa);   // rare: a count >= 128 somewhere in the tile
+        qb = clamp127(qb);
+    }
+    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+    uint32_t vlo4 = 0, vhi4 = 0;
+    if (!FULLT) {
+        const int p0 = ts + lane * 32;
+        vlo4 = (uint32_t)min(max(start - p0, 0), 32) * 0x01010101u;   // valid symbols of this lane: [vlo, vhi)
+        vhi4 = (uint32_t)min(max(end - p0, 0), 32) * 0x01010101u;
+    }
+    uint32_t qc[8], ql[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t g = w[j] + satk;
+        const uint32_t m = byte_msb_mask(g);
+        uint32_t ws = (w[j] & ~m) | (satv & m);
+        if (!FULLT) {
+            const uint32_t iv = (0x03020100u + 0x04040404u * (uint32_t)j) | 0x80808080u;   // symbol indices of this word, bit 7 set
+            const uint32_t ok = (iv - vlo4) & ~(iv - vhi4);                                  // bit 7: vlo <= index < vhi
+            const uint32_t vm = byte_msb_mask(ok);
+            ws = (ws & vm) | (nullv & ~vm);
+        }
+        const uint32_t prod = ws * mult;
+        const uint32_t a0 = __byte_perm(prod, lutp_saddr, 0x7651), a1 = __byte_perm(prod, lutp_saddr, 0x7653);
+        const uint32_t c0 = lds_u16(a0), l0 = lds_u8_256(a0), c1 = lds_u16(a1), l1 = lds_u8_256(a1);
+        qc[j] = (c0 << l1) | c1;
+        ql[j] = l0 + l1;
+    }
+    unsigned long long oc[4];
+    uint32_t ol[4], nb = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        oc[j] = ((unsigned long long)qc[2 * j] << ql[2 * j + 1]) | qc[2 * j + 1];
+        ol[j] = ql[2 * j] + ql[2 * j + 1];
+        nb += ol[j];
+    }
+    const uint32_t incl = warp_incl_scan_p(nb);
+    const uint32_t Pnew = Pbits + __shfl_sync(FULL, incl, 31);
+    uint32_t pos = Pbits + incl - nb;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (oc[j] != 0) {   // zero bits need no write: the ring is zero
+            const unsigned long long A = oc[j] << (64 - ol[j]);
+            const uint32_t Ahi = (uint32_t)(A >> 32), Alo = (uint32_t)A;
+            const uint32_t sh = pos & 31, wi = pos >> 5;
+            const uint32_t W0 = Ahi >> sh;
+            const uint32_t W1 = __funnelshift_r(Alo, Ahi, sh);
+            const uint32_t W2 = __funnelshift_r(0u, Alo, sh);
+            if (W0) atomicOr(&s_ring[wi & RM], W0);
+            if (W1) atomicOr(&s_ring[(wi + 1) & RM], W1);
+            if (W2) atomicOr(&s_ring[(wi + 2) & RM], W2);
+        }
+        pos += ol[j];
+    }
+    Pbits = Pnew;
+}
+
+template <int SV>
+__global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_constant__ EncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    using SM = EncPairSmem;
+    constexpr uint32_t RM = SM::RW - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sm = smem_raw + warp * SM::PER_WARP;
+    uint8_t* s_in = sm + SM::IN;
+    const uint32_t lutp_saddr = smem_u32(sm + SM::LUTP);
+    uint32_t* s_ring = reinterpret_cast<uint32_t*>(sm + SM::RING);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm + SM::BARS);
+
+    const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
+    const int K = T->K;
+    if (T->S != SV || SV != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 8 || T->encp_off == 0 || (lutp_saddr & 255u)) {
+        if (threadIdx.x == 0) *P.overflow = 2;   // launch configuration does not match the table block
+        return;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < ENC_NST; ++i) mbar_init(&s_bar[i], 1);
+        fence_barrier_init();
+    }
+    for (int i = lane; i < SM::RW; i += 32) s_ring[i] = 0;
+    __syncwarp();
+    const uint4* g_encp = reinterpret_cast<const uint4*>(P.tab + T->encp_off);
+    const uint32_t slot_units = (uint32_t)min((long long)(P.slot_bytes >> 4), 0x7FFFFFFFll);
+
+    const int gwarp = blockIdx.x * ENC_WARPS + warp, nwarps = gridDim.x * ENC_WARPS;
+    uint32_t slot = 0, parity = 0;
+    int cur_combo = -1;
+
+    for (int c = gwarp; c < P.L.C; c += nwarps) {
+        const int n = ch_len(P.L, c);
+        const int start = P.start[c];
+        const int end = min(P.end[c], n);
+        uint32_t Pbits = 0;
+        if (end > start && start >= 0) {
+            const int combo = (int)P.peak[c] * K + (int)P.enc[c];
+            if (combo != cur_combo) {   // this (peak, codebook row) pair's table: 512 B
+                __syncwarp();
+                reinterpret_cast<uint4*>(sm + SM::LUTP)[lane] = g_encp[(size_t)combo * 32 + lane];
+                cur_combo = combo;
+                __syncwarp();
+            }
+            const uint8_t* row = P.L.sym + ch_off(P.L, c);
+            const int A0 = start & ~(TILE - 1);
+            const int nt = (end - A0 + TILE - 1) / TILE;
+            const int rd_end = (end + 15) & ~15;
+            uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride;
+            uint8_t* out = P.stream + (size_t)c * P.slot_bytes;
+
+            if (lane == 0) {
+                uint32_t s2 = slot;
+                const int npro = nt < ENC_NST ? nt : ENC_NST;
+                for (int t = 0; t < npro; ++t) {
+                    const int ts = A0 + t * TILE;
+                    const uint32_t bytes = (uint32_t)min(TILE, rd_end - ts);
+                    mbar_expect_tx(&s_bar[s2], bytes);
+                    tma_load_1d(s_in + s2 * TILE, row + ts, bytes, &s_bar[s2]);
+                    s2 = (s2 + 1) & (ENC_NST - 1);
+                }
+            }
+
+            int ts = A0;
+            for (int t = 0; t < nt; ++t, ts += TILE) {
+                mbar_wait(&s_bar[slot], parity);
+                const uint8_t* tile = s_in + slot * TILE + lane * 32;
+                const uint32_t Pold = Pbits;
+                if (lane == 0) co[t] = Pbits;
+                const bool full = (ts >= start) && (ts + TILE <= end);       // warp-uniform
+                if (full) enc_pair_tile<SV, true, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
+                else enc_pair_tile<SV, false, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
+                __syncwarp();
+                for (uint32_t b = Pold; (b >> 7) < (Pbits >> 7); b += 32 * 128)   // up to 64 units per tile
+                    flush_units_z<RM>(s_ring, out, b, Pbits, slot_units, P.overflow, lane);
+                __syncwarp();
+                if (lane == 0 && t + ENC_NST < nt) {
+                    const int ts2 = ts + ENC_NST * TILE;
+                    const uint32_t bytes = (uint32_t)min(TILE, rd_end - ts2);
+                    mbar_expect_tx(&s_bar[slot], bytes);
+                    tma_load_1d(s_in + slot * TILE, row + ts2, bytes, &s_bar[slot]);
+                }
+                slot = (slot + 1) & (ENC_NST - 1);
+                parity ^= (slot == 0);
+            }
+            // last partial unit (zero padded: the ring holds zeros past the last bit), then leave the ring clean
+            if (Pbits & 127) {
+                const uint32_t u = Pbits >> 7;
+                if (lane == 0) {
+                    uint4* rp = reinterpret_cast<uint4*>(&s_ring[(u * 4) & RM]);
+                    uint4 v4 = *rp;
+                    *rp = make_uint4(0, 0, 0, 0);
+                    if (u < slot_units) {
+                        v4.x = bswap32(v4.x); v4.y = bswap32(v4.y); v4.z = bswap32(v4.z); v4.w = bswap32(v4.w);
+                        *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
+                    } else {
+                        *P.overflow = 1;
+                    }
+                }
+            }
             __syncwarp();
         }
         if (lane == 0) P.total_bits[c] = Pbits;
