@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
 // ---------------------------------------------------------------------------------------------
 // pair encoder (Lmax <= 8: every SCLV table up to S = 9)
 // ---------------------------------------------------------------------------------------------
-// Same tiling as the general encoder (warp per channel, 1024-symbol tiles, lane = 32 consecutive symbols, TMA ring),
+// Warp per channel, 2048-symbol tiles (two chunks; lane = 32 consecutive symbols of each), TMA ring,
 // but the per-symbol work follows the fast encoder:
 //   * bytes are saturated with the carry-free SWAR sequence (add on the FMA pipe, PRMT sign-replicate mask, LOP3);
 //   * one multiply by 2 | 2(S+1) << 8 turns the four symbols of a word into two byte offsets (bytes 1 and 3) of
@@ -576,14 +576,16 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
 //     bit offsets; every piece is OR-ed into a zeroed staging ring with shared-memory atomics -- words that are
 //     all zero (the common codeword of the most frequent symbol is '0') are not touched at all; the flush writes
 //     complete 128-bit units with coalesced 16-byte stores and re-zeroes what it has read.
+constexpr int EP_NG = 2;                 // 1024-symbol chunks per warp tile
+constexpr int EP_TILE = EP_NG * TILE;
+constexpr int EP_NST = 2;                // TMA stages per warp
 struct EncPairSmem {
-    static constexpr int RW = 512;                              // staging ring words: 1024 symbols * 8 bits = 256 words + the open unit
-    static constexpr int IN = 0;                                // ENC_NST * TILE bytes
-    static constexpr int LUTP = IN + ENC_NST * TILE;            // 512 B, 256-byte aligned: codes, then lengths
-    static constexpr int LUT1 = LUTP + 512;
-    static constexpr int RING = LUT1 + 64;
+    static constexpr int RW = 1024;                             // staging ring words: 2048 symbols * 8 bits = 512 words + the open unit
+    static constexpr int IN = 0;                                // EP_NST * EP_TILE bytes
+    static constexpr int LUTP = IN + EP_NST * EP_TILE;          // 512 B, 256-byte aligned: codes, then lengths
+    static constexpr int RING = LUTP + 512;
     static constexpr int BARS = RING + RW * 4;
-    static constexpr int PER_WARP = (BARS + ENC_NST * 8 + 511) / 512 * 512;
+    static constexpr int PER_WARP = (BARS + EP_NST * 8 + 511) / 512 * 512;
 };
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
@@ -610,70 +612,87 @@ __device__ __forceinline__ void flush_units_z(uint32_t* s_ring, uint8_t* out, ui
     }
 }
 
+// One 2048-symbol tile: lane l codes symbols [32l, 32l+32) of each of the tile's two chunks.  Returns the bit
+// count of the first chunk (the second chunk's offset).
 template <int SV, bool FULLT, uint32_t RM>
-__device__ __forceinline__ void enc_pair_tile(const uint8_t* tile, uint32_t lutp_saddr, int ts, int start, int end, int lane,
-                                              uint32_t* s_ring, uint32_t& Pbits) {
+__device__ __forceinline__ uint32_t enc_pair_tile(const uint8_t* tile, uint32_t lutp_saddr, int ts, int start, int end, int lane,
+                                                  uint32_t* s_ring, uint32_t& Pbits) {
     constexpr uint32_t satk = (uint32_t)(0x7F - (SV - 1)) * 0x01010101u;
     constexpr uint32_t satv = (uint32_t)(SV - 1) * 0x01010101u;
     constexpr uint32_t nullv = (uint32_t)SV * 0x01010101u;
     constexpr uint32_t mult = 2u | ((uint32_t)(2 * (SV + 1)) << 8);
-    uint4 qa = *reinterpret_cast<const uint4*>(tile), qb = *reinterpret_cast<const uint4*>(tile + 16);
-    if (__any_sync(FULL, (((qa.x | qa.y) | (qa.z | qa.w) | (qb.x | qb.y) | (qb.z | qb.w)) & 0x80808080u) != 0)) {
-        qa = clamp127(qa);   // rare: a count >= 128 somewhere in the tile
-        qb = clamp127(qb);
-    }
-    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-    uint32_t vlo4 = 0, vhi4 = 0;
-    if (!FULLT) {
-        const int p0 = ts + lane * 32;
-        vlo4 = (uint32_t)min(max(start - p0, 0), 32) * 0x01010101u;   // valid symbols of this lane: [vlo, vhi)
-        vhi4 = (uint32_t)min(max(end - p0, 0), 32) * 0x01010101u;
-    }
-    uint32_t qc[8], ql[8];
+    uint4 q[2 * EP_NG];
+    uint32_t any_hi = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t g = w[j] + satk;
-        const uint32_t m = byte_msb_mask(g);
-        uint32_t ws = (w[j] & ~m) | (satv & m);
+    for (int g = 0; g < EP_NG; ++g) {
+        q[2 * g] = *reinterpret_cast<const uint4*>(tile + g * TILE);
+        q[2 * g + 1] = *reinterpret_cast<const uint4*>(tile + g * TILE + 16);
+        any_hi |= (q[2 * g].x | q[2 * g].y) | (q[2 * g].z | q[2 * g].w) | (q[2 * g + 1].x | q[2 * g + 1].y) | (q[2 * g + 1].z | q[2 * g + 1].w);
+    }
+    if (__any_sync(FULL, (any_hi & 0x80808080u) != 0)) {   // rare: a count >= 128 somewhere in the tile
+#pragma unroll
+        for (int i = 0; i < 2 * EP_NG; ++i) q[i] = clamp127(q[i]);
+    }
+    unsigned long long oc[4 * EP_NG];
+    uint32_t ol[4 * EP_NG], nbp = 0;                      // nbp: bit counts of the two chunks, 16 bits each
+#pragma unroll
+    for (int g = 0; g < EP_NG; ++g) {
+        const uint32_t w[8] = {q[2 * g].x, q[2 * g].y, q[2 * g].z, q[2 * g].w, q[2 * g + 1].x, q[2 * g + 1].y, q[2 * g + 1].z, q[2 * g + 1].w};
+        uint32_t vlo4 = 0, vhi4 = 0;
         if (!FULLT) {
-            const uint32_t iv = (0x03020100u + 0x04040404u * (uint32_t)j) | 0x80808080u;   // symbol indices of this word, bit 7 set
-            const uint32_t ok = (iv - vlo4) & ~(iv - vhi4);                                  // bit 7: vlo <= index < vhi
-            const uint32_t vm = byte_msb_mask(ok);
-            ws = (ws & vm) | (nullv & ~vm);
+            const int p0 = ts + g * TILE + lane * 32;
+            vlo4 = (uint32_t)min(max(start - p0, 0), 32) * 0x01010101u;   // valid symbols of this lane: [vlo, vhi)
+            vhi4 = (uint32_t)min(max(end - p0, 0), 32) * 0x01010101u;
         }
-        const uint32_t prod = ws * mult;
-        const uint32_t a0 = __byte_perm(prod, lutp_saddr, 0x7651), a1 = __byte_perm(prod, lutp_saddr, 0x7653);
-        const uint32_t c0 = lds_u16(a0), l0 = lds_u8_256(a0), c1 = lds_u16(a1), l1 = lds_u8_256(a1);
-        qc[j] = (c0 << l1) | c1;
-        ql[j] = l0 + l1;
-    }
-    unsigned long long oc[4];
-    uint32_t ol[4], nb = 0;
+        uint32_t qc[8], ql[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        oc[j] = ((unsigned long long)qc[2 * j] << ql[2 * j + 1]) | qc[2 * j + 1];
-        ol[j] = ql[2 * j] + ql[2 * j + 1];
-        nb += ol[j];
-    }
-    const uint32_t incl = warp_incl_scan_p(nb);
-    const uint32_t Pnew = Pbits + __shfl_sync(FULL, incl, 31);
-    uint32_t pos = Pbits + incl - nb;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (oc[j] != 0) {   // zero bits need no write: the ring is zero
-            const unsigned long long A = oc[j] << (64 - ol[j]);
-            const uint32_t Ahi = (uint32_t)(A >> 32), Alo = (uint32_t)A;
-            const uint32_t sh = pos & 31, wi = pos >> 5;
-            const uint32_t W0 = Ahi >> sh;
-            const uint32_t W1 = __funnelshift_r(Alo, Ahi, sh);
-            const uint32_t W2 = __funnelshift_r(0u, Alo, sh);
-            if (W0) atomicOr(&s_ring[wi & RM], W0);
-            if (W1) atomicOr(&s_ring[(wi + 1) & RM], W1);
-            if (W2) atomicOr(&s_ring[(wi + 2) & RM], W2);
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t gg = w[j] + satk;
+            const uint32_t m = byte_msb_mask(gg);
+            uint32_t ws = (w[j] & ~m) | (satv & m);
+            if (!FULLT) {
+                const uint32_t iv = (0x03020100u + 0x04040404u * (uint32_t)j) | 0x80808080u;   // symbol indices of this word, bit 7 set
+                const uint32_t ok = (iv - vlo4) & ~(iv - vhi4);                                  // bit 7: vlo <= index < vhi
+                const uint32_t vm = byte_msb_mask(ok);
+                ws = (ws & vm) | (nullv & ~vm);
+            }
+            const uint32_t prod = ws * mult;
+            const uint32_t a0 = __byte_perm(prod, lutp_saddr, 0x7651), a1 = __byte_perm(prod, lutp_saddr, 0x7653);
+            const uint32_t c0 = lds_u16(a0), l0 = lds_u8_256(a0), c1 = lds_u16(a1), l1 = lds_u8_256(a1);
+            qc[j] = (c0 << l1) | c1;
+            ql[j] = l0 + l1;
         }
-        pos += ol[j];
+        uint32_t nb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            oc[4 * g + j] = ((unsigned long long)qc[2 * j] << ql[2 * j + 1]) | qc[2 * j + 1];
+            ol[4 * g + j] = ql[2 * j] + ql[2 * j + 1];
+            nb += ol[4 * g + j];
+        }
+        nbp |= nb << (16 * g);
     }
-    Pbits = Pnew;
+    const uint32_t incl = warp_incl_scan_p(nbp);          // both chunks at once: every sum < 2^16
+    const uint32_t tot = __shfl_sync(FULL, incl, 31);
+    const uint32_t excl = incl - nbp;
+    const uint32_t tot0 = tot & 0xFFFFu;
+    uint32_t pos[EP_NG] = {Pbits + (excl & 0xFFFFu), Pbits + tot0 + (excl >> 16)};
+#pragma unroll
+    for (int i = 0; i < 4 * EP_NG; ++i) {
+        // zero bits need no write (the ring is zero); an empty piece has oc == 0, so its shift amount does not matter
+        const unsigned long long A = oc[i] << ((64 - ol[i]) & 63);
+        const uint32_t Ahi = (uint32_t)(A >> 32), Alo = (uint32_t)A;
+        const uint32_t p = pos[i >> 2];
+        const uint32_t sh = p & 31, wi = p >> 5;
+        const uint32_t W0 = Ahi >> sh;
+        const uint32_t W1 = __funnelshift_r(Alo, Ahi, sh);
+        const uint32_t W2 = __funnelshift_r(0u, Alo, sh);
+        if (W0) atomicOr(&s_ring[wi & RM], W0);
+        if (W1) atomicOr(&s_ring[(wi + 1) & RM], W1);
+        if (W2) atomicOr(&s_ring[(wi + 2) & RM], W2);
+        pos[i >> 2] = p + ol[i];
+    }
+    Pbits += tot0 + (tot >> 16);
+    return tot0;
 }
 
 template <int SV>
@@ -696,7 +715,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
     }
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < ENC_NST; ++i) mbar_init(&s_bar[i], 1);
+        for (int i = 0; i < EP_NST; ++i) mbar_init(&s_bar[i], 1);
         fence_barrier_init();
     }
     for (int i = lane; i < SM::RW; i += 32) s_ring[i] = 0;
@@ -722,59 +741,62 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
                 __syncwarp();
             }
             const uint8_t* row = P.L.sym + ch_off(P.L, c);
-            const int A0 = start & ~(TILE - 1);
-            const int nt = (end - A0 + TILE - 1) / TILE;
+            const int A0 = start & ~(EP_TILE - 1);
+            const int nt = (end - A0 + EP_TILE - 1) / EP_TILE;
             const int rd_end = (end + 15) & ~15;
-            uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride;
+            // chunk (1024-symbol) side info: tile t holds chunks 2t and 2t+1 counted from A0, numbered from start/1024
+            uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride + (A0 / TILE - start / TILE);
             uint8_t* out = P.stream + (size_t)c * P.slot_bytes;
 
             if (lane == 0) {
                 uint32_t s2 = slot;
-                const int npro = nt < ENC_NST ? nt : ENC_NST;
+                const int npro = nt < EP_NST ? nt : EP_NST;
                 for (int t = 0; t < npro; ++t) {
-                    const int ts = A0 + t * TILE;
-                    const uint32_t bytes = (uint32_t)min(TILE, rd_end - ts);
+                    const int ts = A0 + t * EP_TILE;
+                    const uint32_t bytes = (uint32_t)min(EP_TILE, rd_end - ts);
                     mbar_expect_tx(&s_bar[s2], bytes);
-                    tma_load_1d(s_in + s2 * TILE, row + ts, bytes, &s_bar[s2]);
-                    s2 = (s2 + 1) & (ENC_NST - 1);
+                    tma_load_1d(s_in + s2 * EP_TILE, row + ts, bytes, &s_bar[s2]);
+                    s2 = (s2 + 1) & (EP_NST - 1);
                 }
             }
 
             int ts = A0;
-            for (int t = 0; t < nt; ++t, ts += TILE) {
+            for (int t = 0; t < nt; ++t, ts += EP_TILE) {
                 mbar_wait(&s_bar[slot], parity);
-                const uint8_t* tile = s_in + slot * TILE + lane * 32;
+                const uint8_t* tile = s_in + slot * EP_TILE + lane * 32;
                 const uint32_t Pold = Pbits;
-                if (lane == 0) co[t] = Pbits;
-                const bool full = (ts >= start) && (ts + TILE <= end);       // warp-uniform
-                if (full) enc_pair_tile<SV, true, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
-                else enc_pair_tile<SV, false, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
+                const bool full = (ts >= start) && (ts + EP_TILE <= end);    // warp-uniform
+                uint32_t tot0;
+                if (full) tot0 = enc_pair_tile<SV, true, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
+                else tot0 = enc_pair_tile<SV, false, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
+                if (lane < EP_NG) {
+                    const int cs = ts + lane * TILE;                         // absolute start of that chunk
+                    if (cs + TILE > start && cs < end) co[EP_NG * t + lane] = Pold + (lane ? tot0 : 0u);
+                }
                 __syncwarp();
-                for (uint32_t b = Pold; (b >> 7) < (Pbits >> 7); b += 32 * 128)   // up to 64 units per tile
+                for (uint32_t b = Pold; (b >> 7) < (Pbits >> 7); b += 32 * 128)   // up to 128 units per tile
                     flush_units_z<RM>(s_ring, out, b, Pbits, slot_units, P.overflow, lane);
                 __syncwarp();
-                if (lane == 0 && t + ENC_NST < nt) {
-                    const int ts2 = ts + ENC_NST * TILE;
-                    const uint32_t bytes = (uint32_t)min(TILE, rd_end - ts2);
+                if (lane == 0 && t + EP_NST < nt) {
+                    const int ts2 = ts + EP_NST * EP_TILE;
+                    const uint32_t bytes = (uint32_t)min(EP_TILE, rd_end - ts2);
                     mbar_expect_tx(&s_bar[slot], bytes);
-                    tma_load_1d(s_in + slot * TILE, row + ts2, bytes, &s_bar[slot]);
+                    tma_load_1d(s_in + slot * EP_TILE, row + ts2, bytes, &s_bar[slot]);
                 }
-                slot = (slot + 1) & (ENC_NST - 1);
+                slot = (slot + 1) & (EP_NST - 1);
                 parity ^= (slot == 0);
             }
             // last partial unit (zero padded: the ring holds zeros past the last bit), then leave the ring clean
-            if (Pbits & 127) {
+            if ((Pbits & 127) && lane == 0) {
                 const uint32_t u = Pbits >> 7;
-                if (lane == 0) {
-                    uint4* rp = reinterpret_cast<uint4*>(&s_ring[(u * 4) & RM]);
-                    uint4 v4 = *rp;
-                    *rp = make_uint4(0, 0, 0, 0);
-                    if (u < slot_units) {
-                        v4.x = bswap32(v4.x); v4.y = bswap32(v4.y); v4.z = bswap32(v4.z); v4.w = bswap32(v4.w);
-                        *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
-                    } else {
-                        *P.overflow = 1;
-                    }
+                uint4* rp = reinterpret_cast<uint4*>(&s_ring[(u * 4) & RM]);
+                uint4 v4 = *rp;
+                *rp = make_uint4(0, 0, 0, 0);
+                if (u < slot_units) {
+                    v4.x = bswap32(v4.x); v4.y = bswap32(v4.y); v4.z = bswap32(v4.z); v4.w = bswap32(v4.w);
+                    *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
+                } else {
+                    *P.overflow = 1;
                 }
             }
             __syncwarp();
