@@ -112,8 +112,17 @@ template <int S>
 __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_constant__ CalibParams P) {
     __shared__ int s_bnd[CAL_WARPS][2 * MUA_MAX_H];
     __shared__ int s_snap[CAL_WARPS][2 * MUA_MAX_H][S];   // [boundary][v] = #{t < b : x_t >= v}, v = 1..S-1
+    __shared__ int s_am[CAL_WARPS][MUA_MAX_H][S], s_pm[CAL_WARPS][MUA_MAX_H][S];   // mapped histograms per history length
+    __shared__ long long s_cost[CAL_WARPS][32];
+    __shared__ int s_k[CAL_WARPS][32];
+    __shared__ uint8_t s_len[MUA_MAX_K][16], s_rank[MUA_MAX_S][16];            // SCLV rows and rank maps of the table block
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * CAL_WARPS + warp;
+    if (!P.train) {
+        for (int i = threadIdx.x; i < MUA_MAX_K * 16; i += blockDim.x) (&s_len[0][0])[i] = (&P.tab->lens[0][0])[i];
+        for (int i = threadIdx.x; i < MUA_MAX_S * 16; i += blockDim.x) (&s_rank[0][0])[i] = (&P.tab->rank[0][0])[i];
+        __syncthreads();
+    }
     if (c >= P.L.C) return;
     const int nH = P.nH, nB = 2 * nH;
     const int n = ch_len(P.L, c);
@@ -176,24 +185,37 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
 #pragma unroll
             for (int j = 0; j < 4; ++j) lo7[j] = w[j] & 0x7F7F7F7Fu;
             if (nextb <= ts + CAL_TILE) {
-                // boundaries inside (ts, ts + CAL_TILE]: snapshot the cumulative counts (rare path)
+                // boundaries inside (ts, ts + CAL_TILE]: snapshot the cumulative counts.  Per tile: the warp totals up to
+                // the tile start (one REDUX per threshold) and, per lane and threshold, 16 flag bits of the lane's 16 bytes;
+                // per boundary: masked popcounts, three thresholds packed per REDUX (a warp total is <= 512 < 2^10).
+                int base[S];
+                uint32_t f16[S];
+#pragma unroll
+                for (int v = 1; v < S; ++v) {
+                    base[v] = __reduce_add_sync(FULL, acc[v] + bytesum4(accb[v]));
+                    uint32_t f = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)   // byte i of word j -> bit 4j + i
+                        f |= ((((ge_mask(w[j], lo7[j], v) >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * j);
+                    f16[v] = f;
+                }
                 for (int bi = 0; bi < nB; ++bi) {
                     const int b = s_bnd[warp][bi];
                     if (b > ts && b <= ts + CAL_TILE && (need_post || bi < nH)) {
                         const int nvalid = min(max(b - p0, 0), 16);
-                        uint32_t m[4];
+                        const uint32_t vm = (1u << nvalid) - 1u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            int nb = min(max(nvalid - 4 * j, 0), 4);
-                            m[j] = nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
-                        }
+                        for (int v0 = 1; v0 < S; v0 += 3) {
+                            uint32_t pk = 0;
 #pragma unroll
-                        for (int v = 1; v < S; ++v) {
-                            int part = acc[v] + bytesum4(accb[v]);
+                            for (int i = 0; i < 3; ++i)
+                                if (v0 + i < S) pk |= (uint32_t)__popc(f16[v0 + i] & vm) << (10 * i);
+                            const uint32_t tot = __reduce_add_sync(FULL, pk);
+                            if (lane == 0) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) part += __popc(ge_mask(w[j], lo7[j], v) & m[j]);
-                            part = __reduce_add_sync(FULL, part);
-                            if (lane == 0) s_snap[warp][bi][v] = part;
+                                for (int i = 0; i < 3; ++i)
+                                    if (v0 + i < S) s_snap[warp][bi][v0 + i] = base[v0 + i] + (int)((tot >> (10 * i)) & 1023u);
+                            }
                         }
                     }
                 }
@@ -213,76 +235,104 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
     }
     __syncwarp();
 
-    // ---- epilogue: lane h handles history length h ----
-    if (lane >= nH) return;
-    const int h = lane;
-    const TabHdr* T = P.tab;
-    const int cut = s_bnd[warp][h];
-    const int end = s_bnd[warp][nH + h];
-    int hist[S], post[S];
-    {
-        int g_prev = cut;   // G_0 = number of samples
+    // ---- epilogue ----
+    // A: lane h < nH turns the snapshots of history length h into the calibration and post-window histograms,
+    //    finds the peak and maps both histograms through the approx-sort rank map;
+    // B: the K cost dot products of every history length are spread over G = 32 / nH lanes each (row k on lane
+    //    k mod G); the (cost, row) pairs meet in shared memory and the first lane of a group takes the first minimum;
+    // C: that lane counts the post-window bits with the chosen row and writes the outputs.
+    int cut = 0, end = 0, p = 0;
+    if (lane < nH) {
+        const int h = lane;
+        cut = s_bnd[warp][h];
+        end = s_bnd[warp][nH + h];
+        int hist[S], post[S];
+        {
+            int g_prev = cut;   // G_0 = number of samples
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            int g_next = s + 1 < S ? s_snap[warp][h][s + 1] : 0;
-            hist[s] = g_prev - g_next;
-            g_prev = g_next;
-        }
-    }
-    const bool has_post = end > 0 && P.mode != MUA_WINDOW_NONE;
-    {
-        int g_prev = has_post ? end - cut : 0;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            int g_next = (has_post && s + 1 < S) ? s_snap[warp][nH + h][s + 1] - s_snap[warp][h][s + 1] : 0;
-            post[s] = g_prev - g_next;
-            g_prev = g_next;
-        }
-    }
-    const size_t o = (size_t)c * nH + h;
-    if (P.train) {
-        // np.flip(np.sort(hist)): descending (get_BR_no_sort.py:147)
-#pragma unroll
-        for (int i = 1; i < S; ++i) {
-#pragma unroll
-            for (int j = S - 1; j >= i; --j) {
-                int a = hist[j - 1], b = hist[j];
-                hist[j - 1] = max(a, b);
-                hist[j] = min(a, b);
+            for (int s = 0; s < S; ++s) {
+                int g_next = s + 1 < S ? s_snap[warp][h][s + 1] : 0;
+                hist[s] = g_prev - g_next;
+                g_prev = g_next;
             }
         }
+        const bool has_post = end > 0 && P.mode != MUA_WINDOW_NONE;
+        {
+            int g_prev = has_post ? end - cut : 0;
 #pragma unroll
-        for (int s = 0; s < S; ++s) P.train_hist[o * S + s] = hist[s];
-        return;
+            for (int s = 0; s < S; ++s) {
+                int g_next = (has_post && s + 1 < S) ? s_snap[warp][nH + h][s + 1] - s_snap[warp][h][s + 1] : 0;
+                post[s] = g_prev - g_next;
+                g_prev = g_next;
+            }
+        }
+        if (P.train) {
+            // np.flip(np.sort(hist)): descending (get_BR_no_sort.py:147)
+#pragma unroll
+            for (int i = 1; i < S; ++i) {
+#pragma unroll
+                for (int j = S - 1; j >= i; --j) {
+                    int a = hist[j - 1], b = hist[j];
+                    hist[j - 1] = max(a, b);
+                    hist[j] = min(a, b);
+                }
+            }
+            const size_t o = (size_t)c * nH + h;
+#pragma unroll
+            for (int s = 0; s < S; ++s) P.train_hist[o * S + s] = hist[s];
+        } else {
+            if (P.use_sort) {   // np.argmax: lowest index on ties (functions_1.py:77)
+                int best = hist[0];
+#pragma unroll
+                for (int s = 1; s < S; ++s)
+                    if (hist[s] > best) { best = hist[s]; p = s; }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {   // mapped histograms: m[rank[s]] = hist[s]
+                const int r = s_rank[p][s];
+                s_am[warp][h][r] = hist[s];
+                s_pm[warp][h][r] = post[s];
+            }
+        }
     }
-    int p = 0;
-    if (P.use_sort) {   // np.argmax: lowest index on ties (functions_1.py:77)
-        int best = hist[0];
+    if (P.train) return;
+    __syncwarp();
+    const int K = P.tab->K;
+    const int G = 32 / nH;                       // lanes per history length (>= 2)
+    const int gh = lane / G, gj = lane - gh * G;
+    {
+        long long best_cost = 0x7FFFFFFFFFFFFFFFll;
+        int enc = -1;
+        if (gh < nH) {
+            int am[S];
 #pragma unroll
-        for (int s = 1; s < S; ++s)
-            if (hist[s] > best) { best = hist[s]; p = s; }
+            for (int r = 0; r < S; ++r) am[r] = s_am[warp][gh][r];
+            for (int k = gj; k < K; k += G) {
+                if (!((P.active >> k) & 1ull)) continue;
+                long long cost = 0;
+#pragma unroll
+                for (int r = 0; r < S; ++r) cost += (long long)am[r] * s_len[k][r];
+                if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
+            }
+        }
+        s_cost[warp][lane] = best_cost;
+        s_k[warp][lane] = enc;
     }
-    int am[S], pm[S];   // mapped histograms: m[rank[s]] = hist[s]
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const int r = T->rank[p][s];
-#pragma unroll
-        for (int rr = 0; rr < S; ++rr)
-            if (rr == r) { am[rr] = hist[s]; pm[rr] = post[s]; }
-    }
+    __syncwarp();
+    if (lane >= nH) return;
+    const int h = lane;
     long long best_cost = 0;
     int enc = -1;
-    for (int k = 0; k < T->K; ++k) {
-        if (!((P.active >> k) & 1ull)) continue;
-        long long cost = 0;
-#pragma unroll
-        for (int r = 0; r < S; ++r) cost += (long long)am[r] * T->lens[k][r];
-        if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
+    for (int j = 0; j < G; ++j) {   // first minimum over the rows: lowest cost, then lowest row index
+        const int k = s_k[warp][h * G + j];
+        const long long cost = s_cost[warp][h * G + j];
+        if (k >= 0 && (enc < 0 || cost < best_cost || (cost == best_cost && k < enc))) { best_cost = cost; enc = k; }
     }
     if (enc < 0) enc = 0;
     long long bits = 0, ns = 0;
 #pragma unroll
-    for (int r = 0; r < S; ++r) { bits += (long long)pm[r] * T->lens[enc][r]; ns += pm[r]; }
+    for (int r = 0; r < S; ++r) { const int pmr = s_pm[warp][h][r]; bits += (long long)pmr * s_len[enc][r]; ns += pmr; }
+    const size_t o = (size_t)c * nH + h;
     if (P.cutoff) P.cutoff[o] = cut;
     if (P.end) P.end[o] = (P.mode == MUA_WINDOW_NONE) ? cut : end;
     if (P.peak) P.peak[o] = (uint8_t)p;
@@ -291,11 +341,11 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
     if (P.nsym) P.nsym[o] = ns;
     if (P.assign_m) {
 #pragma unroll
-        for (int r = 0; r < S; ++r) P.assign_m[o * S + r] = am[r];
+        for (int r = 0; r < S; ++r) P.assign_m[o * S + r] = s_am[warp][h][r];
     }
     if (P.post_m) {
 #pragma unroll
-        for (int r = 0; r < S; ++r) P.post_m[o * S + r] = pm[r];
+        for (int r = 0; r < S; ++r) P.post_m[o * S + r] = s_pm[warp][h][r];
     }
 }
 
