@@ -146,8 +146,9 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
     __syncwarp();
     // the post window is only scanned when a post-window output was asked for
     const bool need_post = P.post_m != nullptr || P.bits != nullptr || P.nsym != nullptr;
-    int scan_end = 0;
-    for (int i = 0; i < (need_post ? nB : nH); ++i) scan_end = max(scan_end, s_bnd[warp][i]);
+    // lane bi owns boundary bi (nB <= 32): 0 or negative = unused
+    const int myb = (lane < (need_post ? nB : nH)) ? s_bnd[warp][lane] : 0;
+    const int scan_end = __reduce_max_sync(FULL, max(myb, 0));
 
     // Counters: per threshold v a packed word of four byte counters (flags of 4 bytes x 4 words per step,
     // flushed into 32-bit counters before they can overflow) -- no POPC on the streaming path.
@@ -157,12 +158,7 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
     for (int v = 0; v < S; ++v) { acc[v] = 0; accb[v] = 0; }
     const int rd_end = (n + 15) & ~15;   // rows are readable up to round_up(len, 16)
     auto next_boundary = [&](int after) {   // smallest boundary > after that still matters (INT_MAX if none)
-        int nb_ = 0x7FFFFFFF;
-        for (int bi = 0; bi < (need_post ? nB : nH); ++bi) {
-            const int b = s_bnd[warp][bi];
-            if (b > after && b < nb_) nb_ = b;
-        }
-        return nb_;
+        return __reduce_min_sync(FULL, myb > after ? myb : 0x7FFFFFFF);
     };
     int nextb = next_boundary(0);
     int since_flush = 0;
@@ -185,37 +181,50 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
 #pragma unroll
             for (int j = 0; j < 4; ++j) lo7[j] = w[j] & 0x7F7F7F7Fu;
             if (nextb <= ts + CAL_TILE) {
-                // boundaries inside (ts, ts + CAL_TILE]: snapshot the cumulative counts.  Per tile: the warp totals up to
-                // the tile start (one REDUX per threshold) and, per lane and threshold, 16 flag bits of the lane's 16 bytes;
-                // per boundary: masked popcounts, three thresholds packed per REDUX (a warp total is <= 512 < 2^10).
+                // Boundaries inside (ts, ts + CAL_TILE]: snapshot the cumulative counts (rare for long rows, everything
+                // for short ones).  All boundaries of the tile are served at once: per threshold the warp total up to the
+                // tile start (one REDUX) and the lane's 16 flag bits; an exclusive scan over lanes of the flag counts,
+                // three thresholds packed per word (a warp total is <= 512 < 2^10); then the lane that owns a boundary
+                // fetches the scan value and the flags of the lane the boundary falls into by shuffle and finishes alone.
                 int base[S];
-                uint32_t f16[S];
+                uint32_t u[S];                     // flag of byte i of word j at bit 8i + j
+                constexpr int NPK = (S - 1 + 2) / 3;
+                uint32_t ex[NPK];
 #pragma unroll
                 for (int v = 1; v < S; ++v) {
                     base[v] = __reduce_add_sync(FULL, acc[v] + bytesum4(accb[v]));
-                    uint32_t f = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)   // byte i of word j -> bit 4j + i
-                        f |= ((((ge_mask(w[j], lo7[j], v) >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * j);
-                    f16[v] = f;
+                    u[v] = (ge_mask(w[0], lo7[0], v) >> 7) | (ge_mask(w[1], lo7[1], v) >> 6) | (ge_mask(w[2], lo7[2], v) >> 5) |
+                           (ge_mask(w[3], lo7[3], v) >> 4);
                 }
-                for (int bi = 0; bi < nB; ++bi) {
-                    const int b = s_bnd[warp][bi];
-                    if (b > ts && b <= ts + CAL_TILE && (need_post || bi < nH)) {
-                        const int nvalid = min(max(b - p0, 0), 16);
-                        const uint32_t vm = (1u << nvalid) - 1u;
 #pragma unroll
-                        for (int v0 = 1; v0 < S; v0 += 3) {
-                            uint32_t pk = 0;
+                for (int g = 0; g < NPK; ++g) {
+                    uint32_t pk = 0;
 #pragma unroll
-                            for (int i = 0; i < 3; ++i)
-                                if (v0 + i < S) pk |= (uint32_t)__popc(f16[v0 + i] & vm) << (10 * i);
-                            const uint32_t tot = __reduce_add_sync(FULL, pk);
-                            if (lane == 0) {
+                    for (int i = 0; i < 3; ++i)
+                        if (1 + 3 * g + i < S) pk |= (uint32_t)__popc(u[1 + 3 * g + i]) << (10 * i);
+                    uint32_t incl = pk;
 #pragma unroll
-                                for (int i = 0; i < 3; ++i)
-                                    if (v0 + i < S) s_snap[warp][bi][v0 + i] = base[v0 + i] + (int)((tot >> (10 * i)) & 1023u);
-                            }
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    ex[g] = incl - pk;
+                }
+                const bool mine = myb > ts && myb <= ts + CAL_TILE;
+                const int q = mine ? myb - ts : 1;            // bytes of the tile before the boundary: 1..512
+                const int L = (q - 1) >> 4;                   // the lane the boundary falls into
+                const int nvalid = q - 16 * L;                // ... and how many of its bytes count: 1..16
+                const int full = nvalid >> 2, part = nvalid & 3;
+                const uint32_t vm = ((1u << full) - 1u) * 0x01010101u | ((1u << full) * (0x01010101u & ((1u << (8 * part)) - 1u)));
+#pragma unroll
+                for (int g = 0; g < NPK; ++g) {
+                    const uint32_t exL = __shfl_sync(FULL, ex[g], L);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int v = 1 + 3 * g + i;
+                        if (v < S) {
+                            const uint32_t uL = __shfl_sync(FULL, u[v], L);
+                            if (mine) s_snap[warp][lane][v] = base[v] + (int)((exL >> (10 * i)) & 1023u) + __popc(uL & vm);
                         }
                     }
                 }
