@@ -14,6 +14,13 @@ MAX_H = 16
 
 _vp, _i32, _i64, _u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
 
+class CalibOut(C.Structure):
+    """struct mua_calib_out (include/mua_b200.h): tables and output buffers of one alphabet size."""
+    _fields_ = [("S", _i32), ("d_tables", _vp), ("active_lo", _u32), ("active_hi", _u32),
+                ("d_cutoff", _vp), ("d_end", _vp), ("d_peak", _vp), ("d_enc", _vp), ("d_assign_m", _vp),
+                ("d_post_m", _vp), ("d_bits", _vp), ("d_nsym", _vp), ("d_train_hist", _vp)]
+
+
 #: every symbol include/mua_b200.h declares -> (restype, argtypes)
 SIGNATURES = {
     "mua_abi_version": (C.c_int, []),
@@ -25,6 +32,8 @@ SIGNATURES = {
     "mua_calibrate": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _u32, _u32,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mua_train_hist": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "mua_calibrate_multi": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _i32, C.POINTER(CalibOut), _i32, _vp]),
+    "mua_train_hist_multi": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, C.POINTER(CalibOut), _i32, _vp]),
     "mua_select_sclv": (C.c_int, [_vp, _i64, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
     "mua_bit_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mua_elim_scores": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),

@@ -81,25 +81,33 @@ void layout_sizes(int S, int K, int Lmax, TabHdr* h) {
     h->total_bytes = align_up(h->dec_off + ((S * K) << h->W) * 4, 512);
 }
 
-template <int S>
+template <int SS, bool MULTI>
 void launch_calibrate(const CalibParams& P, cudaStream_t st) {
     const int grid = (P.L.C + CAL_WARPS - 1) / CAL_WARPS;
-    k_calibrate<S><<<grid, CAL_WARPS * 32, 0, st>>>(P);
+    k_calibrate<SS, MULTI><<<grid, CAL_WARPS * 32, 0, st>>>(P);
 }
 
+// one alphabet size: the scan counts exactly its thresholds; several: one scan with the thresholds of the largest
 int dispatch_calibrate(const CalibParams& P, cudaStream_t st) {
     if (P.L.C == 0) return MUA_OK;
-    switch (P.S) {
-        case 2: launch_calibrate<2>(P, st); break;
-        case 3: launch_calibrate<3>(P, st); break;
-        case 4: launch_calibrate<4>(P, st); break;
-        case 5: launch_calibrate<5>(P, st); break;
-        case 6: launch_calibrate<6>(P, st); break;
-        case 7: launch_calibrate<7>(P, st); break;
-        case 8: launch_calibrate<8>(P, st); break;
-        case 9: launch_calibrate<9>(P, st); break;
-        case 10: launch_calibrate<10>(P, st); break;
-        default: return fail(MUA_E_INVALID, "S=%d outside 2..10", P.S);
+    if (P.nS == 1) {
+        switch (P.out[0].S) {
+            case 2: launch_calibrate<2, false>(P, st); break;
+            case 3: launch_calibrate<3, false>(P, st); break;
+            case 4: launch_calibrate<4, false>(P, st); break;
+            case 5: launch_calibrate<5, false>(P, st); break;
+            case 6: launch_calibrate<6, false>(P, st); break;
+            case 7: launch_calibrate<7, false>(P, st); break;
+            case 8: launch_calibrate<8, false>(P, st); break;
+            case 9: launch_calibrate<9, false>(P, st); break;
+            case 10: launch_calibrate<10, false>(P, st); break;
+            default: return fail(MUA_E_INVALID, "S=%d outside 2..10", P.out[0].S);
+        }
+    } else {
+        int smax = 0;
+        for (int i = 0; i < P.nS; ++i) smax = P.out[i].S > smax ? P.out[i].S : smax;
+        if (smax <= 6) launch_calibrate<6, true>(P, st);
+        else launch_calibrate<10, true>(P, st);
     }
     CHECK_LAUNCH("k_calibrate");
     return MUA_OK;
@@ -217,38 +225,68 @@ int mua_calibrate(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_l
                   const int32_t* h_H, int32_t nH, int32_t use_sort, int32_t window_mode, const void* d_tables, uint32_t active_lo,
                   uint32_t active_hi, int32_t* d_cutoff, int32_t* d_end, uint8_t* d_peak, uint8_t* d_enc, int32_t* d_assign_m,
                   int32_t* d_post_m, int64_t* d_bits, int64_t* d_nsym, void* stream) {
+    mua_calib_out o;
+    memset(&o, 0, sizeof(o));
+    o.S = S; o.d_tables = d_tables; o.active_lo = active_lo; o.active_hi = active_hi;
+    o.d_cutoff = d_cutoff; o.d_end = d_end; o.d_peak = d_peak; o.d_enc = d_enc;
+    o.d_assign_m = d_assign_m; o.d_post_m = d_post_m; o.d_bits = d_bits; o.d_nsym = d_nsym;
+    return mua_calibrate_multi(d_sym, d_off, d_len, stride, T, C, h_H, nH, use_sort, window_mode, &o, 1, stream);
+}
+
+int mua_calibrate_multi(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C,
+                        const int32_t* h_H, int32_t nH, int32_t use_sort, int32_t window_mode, const mua_calib_out* h_outs,
+                        int32_t nS, void* stream) {
     int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
     if (rc) return rc;
-    REQUIRE(S >= 2 && S <= MUA_MAX_S, "S=%d outside 2..10", S);
     REQUIRE(h_H && nH >= 1 && nH <= MUA_MAX_H, "nH outside 1..%d", MUA_MAX_H);
     REQUIRE(window_mode >= 0 && window_mode <= 2, "bad window_mode");
-    REQUIRE(d_tables, "d_tables is NULL");
+    REQUIRE(h_outs && nS >= 1 && nS <= CAL_MAX_NS, "nS outside 1..%d", CAL_MAX_NS);
     CalibParams P;
     memset(&P, 0, sizeof(P));
     P.L = Layout{d_sym, d_off, d_len, stride, T, C};
-    P.S = S; P.nH = nH; P.use_sort = use_sort; P.mode = window_mode; P.train = 0;
+    P.nH = nH; P.use_sort = use_sort; P.mode = window_mode; P.train = 0; P.nS = nS;
     for (int i = 0; i < nH; ++i) P.H[i] = h_H[i];
-    P.tab = reinterpret_cast<const TabHdr*>(d_tables);
-    P.active = ((unsigned long long)active_hi << 32) | active_lo;
-    REQUIRE(P.active != 0, "no active SCLV row");
-    P.cutoff = d_cutoff; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
-    P.assign_m = d_assign_m; P.post_m = d_post_m; P.bits = d_bits; P.nsym = d_nsym;
+    for (int i = 0; i < nS; ++i) {
+        const mua_calib_out& o = h_outs[i];
+        REQUIRE(o.S >= 2 && o.S <= MUA_MAX_S, "S=%d outside 2..10", o.S);
+        REQUIRE(o.d_tables, "d_tables is NULL");
+        CalOut& q = P.out[i];
+        q.S = o.S;
+        q.tab = reinterpret_cast<const TabHdr*>(o.d_tables);
+        q.active = ((unsigned long long)o.active_hi << 32) | o.active_lo;
+        REQUIRE(q.active != 0, "no active SCLV row");
+        q.cutoff = o.d_cutoff; q.end = o.d_end; q.peak = o.d_peak; q.enc = o.d_enc;
+        q.assign_m = o.d_assign_m; q.post_m = o.d_post_m; q.bits = o.d_bits; q.nsym = o.d_nsym;
+        if (o.d_post_m || o.d_bits || o.d_nsym) P.need_post = 1;
+    }
     return dispatch_calibrate(P, (cudaStream_t)stream);
 }
 
 int mua_train_hist(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C, int32_t S,
                    int32_t* d_hist_sorted, void* stream) {
+    mua_calib_out o;
+    memset(&o, 0, sizeof(o));
+    o.S = S; o.d_train_hist = d_hist_sorted;
+    return mua_train_hist_multi(d_sym, d_off, d_len, stride, T, C, &o, 1, stream);
+}
+
+int mua_train_hist_multi(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C,
+                         const mua_calib_out* h_outs, int32_t nS, void* stream) {
     int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
     if (rc) return rc;
-    REQUIRE(S >= 2 && S <= MUA_MAX_S, "S=%d outside 2..10", S);
-    REQUIRE(d_hist_sorted, "d_hist_sorted is NULL");
+    REQUIRE(h_outs && nS >= 1 && nS <= CAL_MAX_NS, "nS outside 1..%d", CAL_MAX_NS);
     CalibParams P;
     memset(&P, 0, sizeof(P));
     P.L = Layout{d_sym, d_off, d_len, stride, T, C};
-    P.S = S; P.nH = 1; P.use_sort = 0; P.mode = MUA_WINDOW_NONE; P.train = 1;
+    P.nH = 1; P.use_sort = 0; P.mode = MUA_WINDOW_NONE; P.train = 1; P.nS = nS;
     P.H[0] = 0x7FFFFFFF;
-    P.active = 1;
-    P.train_hist = d_hist_sorted;
+    for (int i = 0; i < nS; ++i) {
+        REQUIRE(h_outs[i].S >= 2 && h_outs[i].S <= MUA_MAX_S, "S=%d outside 2..10", h_outs[i].S);
+        REQUIRE(h_outs[i].d_train_hist, "d_train_hist is NULL");
+        P.out[i].S = h_outs[i].S;
+        P.out[i].active = 1;
+        P.out[i].train_hist = h_outs[i].d_train_hist;
+    }
     return dispatch_calibrate(P, (cudaStream_t)stream);
 }
 

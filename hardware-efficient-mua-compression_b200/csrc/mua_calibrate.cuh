@@ -88,10 +88,14 @@ __device__ __forceinline__ int bytesum4(uint32_t x) {
 // ---------------------------------------------------------------------------------------------
 // calibrate: warp per channel
 // ---------------------------------------------------------------------------------------------
-struct CalibParams {
-    Layout L;
-    int32_t S, nH, use_sort, mode, train;
-    int32_t H[MUA_MAX_H];
+// One scan of a channel serves every history length AND every alphabet size that was asked for: the scan counts
+// #{x >= v} for v = 1..SS-1 (SS = largest alphabet), and the histogram of the data saturated at S-1 is
+// hist_S[s] = G_s - G_{s+1} (s < S-1), hist_S[S-1] = G_{S-1} -- saturation never changes whether x >= v for v < S.
+// The reference re-reads and re-saturates every channel for each S of its sweep (get_BR_no_sort.py:107, :143, :164).
+constexpr int CAL_MAX_NS = 9;   // alphabet sizes per launch (2..10)
+
+struct CalOut {                 // outputs and tables of one alphabet size
+    int32_t S;
     const TabHdr* tab;
     unsigned long long active;
     int32_t* cutoff;
@@ -105,25 +109,169 @@ struct CalibParams {
     int32_t* train_hist;
 };
 
+struct CalibParams {
+    Layout L;
+    int32_t nH, use_sort, mode, train, nS, need_post;
+    int32_t H[MUA_MAX_H];
+    CalOut out[CAL_MAX_NS];
+};
+
 constexpr int CAL_WARPS = 4;
 constexpr int CAL_TILE = 512;   // bytes per warp step (16 B per lane)
 
-template <int S>
+struct CalSmem {                // per warp
+    int bnd[2 * MUA_MAX_H];
+    int am[MUA_MAX_H][MUA_MAX_S], pm[MUA_MAX_H][MUA_MAX_S];   // mapped histograms per history length
+    long long cost[32];
+    int k[32];
+    uint4 len[MUA_MAX_K], rank[MUA_MAX_S];                    // SCLV rows and rank maps of the current table block (16 B rows)
+};
+
+// Epilogue of one alphabet size S (snapshots counted with SS >= S thresholds):
+//   A: lane h < nH turns the snapshots of history length h into the calibration and post-window histograms,
+//      finds the peak and maps both histograms through the approx-sort rank map;
+//   B: the K cost dot products of every history length are spread over G = 32 / nH lanes each (row k on lane
+//      k mod G); the (cost, row) pairs meet in shared memory and the first lane of a group takes the first minimum;
+//   C: that lane counts the post-window bits with the chosen row and writes the outputs.
+template <int S, int SS>
+__device__ __forceinline__ void cal_epilogue(const CalibParams& P, const CalOut& O, int c, int lane, CalSmem& W, const int (*snap)[SS]) {
+    const int nH = P.nH;
+    if (!P.train) {   // this alphabet's SCLV rows and rank maps -> shared memory of this warp
+        __syncwarp();
+        const uint4* gl = reinterpret_cast<const uint4*>(&O.tab->lens[0][0]);
+        const uint4* gr = reinterpret_cast<const uint4*>(&O.tab->rank[0][0]);
+        for (int i = lane; i < MUA_MAX_K; i += 32) W.len[i] = gl[i];
+        if (lane < MUA_MAX_S) W.rank[lane] = gr[lane];
+        __syncwarp();
+    }
+    const uint8_t(*s_len)[16] = reinterpret_cast<const uint8_t(*)[16]>(W.len);
+    const uint8_t(*s_rank)[16] = reinterpret_cast<const uint8_t(*)[16]>(W.rank);
+    int cut = 0, end = 0, p = 0;
+    if (lane < nH) {
+        const int h = lane;
+        cut = W.bnd[h];
+        end = W.bnd[nH + h];
+        int hist[S], post[S];
+        {
+            int g_prev = cut;   // G_0 = number of samples
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int g_next = s + 1 < S ? snap[h][s + 1] : 0;
+                hist[s] = g_prev - g_next;
+                g_prev = g_next;
+            }
+        }
+        const bool has_post = end > 0 && P.mode != MUA_WINDOW_NONE;
+        {
+            int g_prev = has_post ? end - cut : 0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int g_next = (has_post && s + 1 < S) ? snap[nH + h][s + 1] - snap[h][s + 1] : 0;
+                post[s] = g_prev - g_next;
+                g_prev = g_next;
+            }
+        }
+        if (P.train) {
+            // np.flip(np.sort(hist)): descending (get_BR_no_sort.py:147)
+#pragma unroll
+            for (int i = 1; i < S; ++i) {
+#pragma unroll
+                for (int j = S - 1; j >= i; --j) {
+                    int a = hist[j - 1], b = hist[j];
+                    hist[j - 1] = max(a, b);
+                    hist[j] = min(a, b);
+                }
+            }
+            const size_t o = (size_t)c * nH + h;
+#pragma unroll
+            for (int s = 0; s < S; ++s) O.train_hist[o * S + s] = hist[s];
+        } else {
+            if (P.use_sort) {   // np.argmax: lowest index on ties (functions_1.py:77)
+                int best = hist[0];
+#pragma unroll
+                for (int s = 1; s < S; ++s)
+                    if (hist[s] > best) { best = hist[s]; p = s; }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {   // mapped histograms: m[rank[s]] = hist[s]
+                const int r = s_rank[p][s];
+                W.am[h][r] = hist[s];
+                W.pm[h][r] = post[s];
+            }
+        }
+    }
+    if (P.train) return;
+    __syncwarp();
+    const int K = O.tab->K;
+    const int G = 32 / nH;                       // lanes per history length (>= 2)
+    const int gh = lane / G, gj = lane - gh * G;
+    {
+        long long best_cost = 0x7FFFFFFFFFFFFFFFll;
+        int enc = -1;
+        if (gh < nH) {
+            int am[S];
+#pragma unroll
+            for (int r = 0; r < S; ++r) am[r] = W.am[gh][r];
+            for (int k = gj; k < K; k += G) {
+                if (!((O.active >> k) & 1ull)) continue;
+                long long cost = 0;
+#pragma unroll
+                for (int r = 0; r < S; ++r) cost += (long long)am[r] * s_len[k][r];
+                if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
+            }
+        }
+        W.cost[lane] = best_cost;
+        W.k[lane] = enc;
+    }
+    __syncwarp();
+    if (lane < nH) {
+        const int h = lane;
+        long long best_cost = 0;
+        int enc = -1;
+        for (int j = 0; j < G; ++j) {   // first minimum over the rows: lowest cost, then lowest row index
+            const int k = W.k[h * G + j];
+            const long long cost = W.cost[h * G + j];
+            if (k >= 0 && (enc < 0 || cost < best_cost || (cost == best_cost && k < enc))) { best_cost = cost; enc = k; }
+        }
+        if (enc < 0) enc = 0;
+        long long bits = 0, ns = 0;
+#pragma unroll
+        for (int r = 0; r < S; ++r) { const int pmr = W.pm[h][r]; bits += (long long)pmr * s_len[enc][r]; ns += pmr; }
+        const size_t o = (size_t)c * nH + h;
+        if (O.cutoff) O.cutoff[o] = cut;
+        if (O.end) O.end[o] = (P.mode == MUA_WINDOW_NONE) ? cut : end;
+        if (O.peak) O.peak[o] = (uint8_t)p;
+        if (O.enc) O.enc[o] = (uint8_t)enc;
+        if (O.bits) O.bits[o] = bits;
+        if (O.nsym) O.nsym[o] = ns;
+        if (O.assign_m) {
+#pragma unroll
+            for (int r = 0; r < S; ++r) O.assign_m[o * S + r] = W.am[h][r];
+        }
+        if (O.post_m) {
+#pragma unroll
+            for (int r = 0; r < S; ++r) O.post_m[o * S + r] = W.pm[h][r];
+        }
+    }
+    __syncwarp();
+}
+
+template <int S, int SS>
+__device__ __forceinline__ void cal_epilogue_if(const CalibParams& P, const CalOut& O, int c, int lane, CalSmem& W, const int (*snap)[SS]) {
+    if constexpr (S <= SS) cal_epilogue<S, SS>(P, O, c, lane, W, snap);
+}
+
+// SS = number of symbol values the scan distinguishes (thresholds 1..SS-1); MULTI: the epilogue runs for every
+// alphabet size in P.out[0..nS) (each <= SS), otherwise for P.out[0] with S == SS.
+template <int SS, bool MULTI>
 __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_constant__ CalibParams P) {
-    __shared__ int s_bnd[CAL_WARPS][2 * MUA_MAX_H];
+    constexpr int S = SS;
     __shared__ int s_snap[CAL_WARPS][2 * MUA_MAX_H][S];   // [boundary][v] = #{t < b : x_t >= v}, v = 1..S-1
-    __shared__ int s_am[CAL_WARPS][MUA_MAX_H][S], s_pm[CAL_WARPS][MUA_MAX_H][S];   // mapped histograms per history length
-    __shared__ long long s_cost[CAL_WARPS][32];
-    __shared__ int s_k[CAL_WARPS][32];
-    __shared__ uint8_t s_len[MUA_MAX_K][16], s_rank[MUA_MAX_S][16];            // SCLV rows and rank maps of the table block
+    __shared__ CalSmem s_w[CAL_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * CAL_WARPS + warp;
-    if (!P.train) {
-        for (int i = threadIdx.x; i < MUA_MAX_K * 16; i += blockDim.x) (&s_len[0][0])[i] = (&P.tab->lens[0][0])[i];
-        for (int i = threadIdx.x; i < MUA_MAX_S * 16; i += blockDim.x) (&s_rank[0][0])[i] = (&P.tab->rank[0][0])[i];
-        __syncthreads();
-    }
     if (c >= P.L.C) return;
+    CalSmem& W = s_w[warp];
     const int nH = P.nH, nB = 2 * nH;
     const int n = ch_len(P.L, c);
     const uint8_t* row = P.L.sym + ch_off(P.L, c);
@@ -139,15 +287,15 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
         } else if (P.mode == MUA_WINDOW_TRUNCATE) {
             end = min(cut + n / 2, n);
         }
-        s_bnd[warp][lane] = cut;
-        s_bnd[warp][nH + lane] = end;
+        W.bnd[lane] = cut;
+        W.bnd[nH + lane] = end;
     }
     for (int i = lane; i < nB * S; i += 32) (&s_snap[warp][0][0])[i] = 0;
     __syncwarp();
     // the post window is only scanned when a post-window output was asked for
-    const bool need_post = P.post_m != nullptr || P.bits != nullptr || P.nsym != nullptr;
+    const bool need_post = P.need_post != 0;
     // lane bi owns boundary bi (nB <= 32): 0 or negative = unused
-    const int myb = (lane < (need_post ? nB : nH)) ? s_bnd[warp][lane] : 0;
+    const int myb = (lane < (need_post ? nB : nH)) ? W.bnd[lane] : 0;
     const int scan_end = __reduce_max_sync(FULL, max(myb, 0));
 
     // Counters: per threshold v a packed word of four byte counters (flags of 4 bytes x 4 words per step,
@@ -244,117 +392,26 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
     }
     __syncwarp();
 
-    // ---- epilogue ----
-    // A: lane h < nH turns the snapshots of history length h into the calibration and post-window histograms,
-    //    finds the peak and maps both histograms through the approx-sort rank map;
-    // B: the K cost dot products of every history length are spread over G = 32 / nH lanes each (row k on lane
-    //    k mod G); the (cost, row) pairs meet in shared memory and the first lane of a group takes the first minimum;
-    // C: that lane counts the post-window bits with the chosen row and writes the outputs.
-    int cut = 0, end = 0, p = 0;
-    if (lane < nH) {
-        const int h = lane;
-        cut = s_bnd[warp][h];
-        end = s_bnd[warp][nH + h];
-        int hist[S], post[S];
-        {
-            int g_prev = cut;   // G_0 = number of samples
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                int g_next = s + 1 < S ? s_snap[warp][h][s + 1] : 0;
-                hist[s] = g_prev - g_next;
-                g_prev = g_next;
+    // ---- epilogue(s) ----
+    const int (*snap)[S] = s_snap[warp];
+    if (!MULTI) {
+        cal_epilogue<S, S>(P, P.out[0], c, lane, W, snap);
+    } else {
+        for (int i = 0; i < P.nS; ++i) {
+            const CalOut& O = P.out[i];
+            switch (O.S) {
+                case 2: cal_epilogue_if<2, S>(P, O, c, lane, W, snap); break;
+                case 3: cal_epilogue_if<3, S>(P, O, c, lane, W, snap); break;
+                case 4: cal_epilogue_if<4, S>(P, O, c, lane, W, snap); break;
+                case 5: cal_epilogue_if<5, S>(P, O, c, lane, W, snap); break;
+                case 6: cal_epilogue_if<6, S>(P, O, c, lane, W, snap); break;
+                case 7: cal_epilogue_if<7, S>(P, O, c, lane, W, snap); break;
+                case 8: cal_epilogue_if<8, S>(P, O, c, lane, W, snap); break;
+                case 9: cal_epilogue_if<9, S>(P, O, c, lane, W, snap); break;
+                case 10: cal_epilogue_if<10, S>(P, O, c, lane, W, snap); break;
+                default: break;
             }
         }
-        const bool has_post = end > 0 && P.mode != MUA_WINDOW_NONE;
-        {
-            int g_prev = has_post ? end - cut : 0;
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                int g_next = (has_post && s + 1 < S) ? s_snap[warp][nH + h][s + 1] - s_snap[warp][h][s + 1] : 0;
-                post[s] = g_prev - g_next;
-                g_prev = g_next;
-            }
-        }
-        if (P.train) {
-            // np.flip(np.sort(hist)): descending (get_BR_no_sort.py:147)
-#pragma unroll
-            for (int i = 1; i < S; ++i) {
-#pragma unroll
-                for (int j = S - 1; j >= i; --j) {
-                    int a = hist[j - 1], b = hist[j];
-                    hist[j - 1] = max(a, b);
-                    hist[j] = min(a, b);
-                }
-            }
-            const size_t o = (size_t)c * nH + h;
-#pragma unroll
-            for (int s = 0; s < S; ++s) P.train_hist[o * S + s] = hist[s];
-        } else {
-            if (P.use_sort) {   // np.argmax: lowest index on ties (functions_1.py:77)
-                int best = hist[0];
-#pragma unroll
-                for (int s = 1; s < S; ++s)
-                    if (hist[s] > best) { best = hist[s]; p = s; }
-            }
-#pragma unroll
-            for (int s = 0; s < S; ++s) {   // mapped histograms: m[rank[s]] = hist[s]
-                const int r = s_rank[p][s];
-                s_am[warp][h][r] = hist[s];
-                s_pm[warp][h][r] = post[s];
-            }
-        }
-    }
-    if (P.train) return;
-    __syncwarp();
-    const int K = P.tab->K;
-    const int G = 32 / nH;                       // lanes per history length (>= 2)
-    const int gh = lane / G, gj = lane - gh * G;
-    {
-        long long best_cost = 0x7FFFFFFFFFFFFFFFll;
-        int enc = -1;
-        if (gh < nH) {
-            int am[S];
-#pragma unroll
-            for (int r = 0; r < S; ++r) am[r] = s_am[warp][gh][r];
-            for (int k = gj; k < K; k += G) {
-                if (!((P.active >> k) & 1ull)) continue;
-                long long cost = 0;
-#pragma unroll
-                for (int r = 0; r < S; ++r) cost += (long long)am[r] * s_len[k][r];
-                if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
-            }
-        }
-        s_cost[warp][lane] = best_cost;
-        s_k[warp][lane] = enc;
-    }
-    __syncwarp();
-    if (lane >= nH) return;
-    const int h = lane;
-    long long best_cost = 0;
-    int enc = -1;
-    for (int j = 0; j < G; ++j) {   // first minimum over the rows: lowest cost, then lowest row index
-        const int k = s_k[warp][h * G + j];
-        const long long cost = s_cost[warp][h * G + j];
-        if (k >= 0 && (enc < 0 || cost < best_cost || (cost == best_cost && k < enc))) { best_cost = cost; enc = k; }
-    }
-    if (enc < 0) enc = 0;
-    long long bits = 0, ns = 0;
-#pragma unroll
-    for (int r = 0; r < S; ++r) { const int pmr = s_pm[warp][h][r]; bits += (long long)pmr * s_len[enc][r]; ns += pmr; }
-    const size_t o = (size_t)c * nH + h;
-    if (P.cutoff) P.cutoff[o] = cut;
-    if (P.end) P.end[o] = (P.mode == MUA_WINDOW_NONE) ? cut : end;
-    if (P.peak) P.peak[o] = (uint8_t)p;
-    if (P.enc) P.enc[o] = (uint8_t)enc;
-    if (P.bits) P.bits[o] = bits;
-    if (P.nsym) P.nsym[o] = ns;
-    if (P.assign_m) {
-#pragma unroll
-        for (int r = 0; r < S; ++r) P.assign_m[o * S + r] = s_am[warp][h][r];
-    }
-    if (P.post_m) {
-#pragma unroll
-        for (int r = 0; r < S; ++r) P.post_m[o * S + r] = s_pm[warp][h][r];
     }
 }
 

@@ -40,15 +40,30 @@ def _br_doubles(bits, nsym, BP):
 def br_sweep_one(train, val, S, BP, use_sort, device="cuda", tables=None, hist_sizes=HIST_SIZES):
     """One (CV, BP, S) cell of get_BR_no_sort.py / get_BR_with_approx_sort.py (:104-331).
     train/val: lists of 1-D uint8 channel arrays.  Returns the dict the reference pickles."""
-    sclvs = (tables or load_sclv_tables())[int(S)]
-    cb = Codebook(S, sclvs, device=device)
-    K, nH, Cv, Ct = cb.K, len(hist_sizes), len(val), len(train)
+    return br_sweep_multi(train, val, [int(S)], BP, use_sort, device, tables, hist_sizes)[int(S)]
+
+
+def br_sweep_multi(train, val, S_values, BP, use_sort, device="cuda", tables=None, hist_sizes=HIST_SIZES):
+    """All alphabet sizes of one (CV, BP) cell: the recordings are uploaded once and read once -- one train-histogram
+    pass and one calibration pass serve every S (the scripts' `for S in range(2, 11)` loop, get_BR_no_sort.py:107,
+    re-saturates and re-counts every channel per S).  Returns {S: the dict the reference pickles}."""
+    S_values = [int(S) for S in S_values]
+    tables = tables or load_sclv_tables()
+    cbs = {S: Codebook(S, tables[S], device=device) for S in S_values}
+    Cv, Ct = len(val), len(train)
     rec_t = P.Recording.from_channels(train, device) if Ct else None
     rec_v = P.Recording.from_channels(val, device) if Cv else None
-    htrain = P.train_hist(rec_t, S) if Ct else torch.zeros((0, S), dtype=torch.int32, device=device)
+    htrains = P.train_hist_multi(rec_t, S_values) if Ct else \
+        {S: torch.zeros((0, S), dtype=torch.int32, device=device) for S in S_values}
+    cals = P.calibrate_multi(rec_v, [cbs[S] for S in S_values], hist_sizes, use_sort=use_sort, window="skip",
+                             want=("cutoff", "end", "assign_m", "post_m")) if Cv else {S: None for S in S_values}
+    return {S: _br_elimination(cbs[S], tables[S], htrains[S], cals[S], val, BP, hist_sizes) for S in S_values}
+
+
+def _br_elimination(cb, sclvs, htrain, cal, val, BP, hist_sizes):
+    """The elimination rounds of one alphabet size (get_BR_no_sort.py:222-322) on the precomputed histograms."""
+    K, nH, Cv = cb.K, len(hist_sizes), len(val)
     if Cv:
-        cal = P.calibrate(rec_v, cb, hist_sizes, use_sort=use_sort, window="skip",
-                          want=("cutoff", "end", "assign_m", "post_m"))
         cut = cal["cutoff"].cpu().numpy().astype(np.int64)
         end = cal["end"].cpu().numpy().astype(np.int64)
         # skipped channels: the scripts keep end = cutoff + len//2 in end_cutoff (:178) even when skipping
@@ -97,8 +112,9 @@ def br_script(all_binned_data, bin_vector, use_sort, seed=None, cv_iterations=(1
     for cv in cv_iterations:
         for b, BP in enumerate(bin_vector):
             train, val = split_channels(all_binned_data[b])
+            cell = br_sweep_multi(train, val, list(S_values), BP, use_sort, device, tables)
             for S in S_values:
-                out[(int(S), int(BP), int(cv))] = br_sweep_one(train, val, int(S), BP, use_sort, device, tables)
+                out[(int(S), int(BP), int(cv))] = cell[int(S)]
     return out
 
 

@@ -24,6 +24,10 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _addr(t: Optional[torch.Tensor]):
+    return None if t is None else int(t.data_ptr())
+
+
 def _round16(v):
     return (int(v) + 15) // 16 * 16
 
@@ -143,6 +147,49 @@ def train_hist(rec: Recording, S: int):
     with torch.cuda.device(rec.device):
         _lib.check(lib.mua_train_hist(*rec.layout_args(), int(S), _ptr(out), _stream()))
     return out
+
+
+def calibrate_multi(rec: Recording, cbs, H, use_sort=True, window="skip",
+                    want=("cutoff", "end", "peak", "enc", "assign_m", "post_m", "bits", "nsym")):
+    """`calibrate` for several alphabet sizes in ONE pass over the recording (mua_calibrate_multi): `cbs` is a list of
+    Codebooks with distinct S; returns {S: dict of tensors as `calibrate` returns}.  The scripts' S loop
+    (get_BR_no_sort.py:107) re-reads every channel per S; here the scan runs once with the thresholds of the largest S."""
+    lib = _lib.load()
+    H = [int(h) for h in np.atleast_1d(H)]
+    nH = len(H)
+    assert 1 <= nH <= _lib.MAX_H and 1 <= len(cbs) <= 9 and len({cb.S for cb in cbs}) == len(cbs)
+    dev = rec.device
+    outs, arr = {}, (_lib.CalibOut * len(cbs))()
+    for i, cb in enumerate(cbs):
+        shapes = {"cutoff": ((rec.C, nH), torch.int32), "end": ((rec.C, nH), torch.int32),
+                  "peak": ((rec.C, nH), torch.uint8), "enc": ((rec.C, nH), torch.uint8),
+                  "assign_m": ((rec.C, nH, cb.S), torch.int32), "post_m": ((rec.C, nH, cb.S), torch.int32),
+                  "bits": ((rec.C, nH), torch.int64), "nsym": ((rec.C, nH), torch.int64)}
+        o = {k: torch.zeros(shapes[k][0], dtype=shapes[k][1], device=dev) for k in want}
+        outs[cb.S] = o
+        lo, hi = _active_words(None, cb)
+        arr[i].S, arr[i].d_tables, arr[i].active_lo, arr[i].active_hi = cb.S, _addr(cb.d_tables), lo, hi
+        for k in shapes:
+            setattr(arr[i], "d_" + k, _addr(o.get(k)))
+    hH = (C.c_int32 * nH)(*H)
+    with torch.cuda.device(dev):
+        la = rec.layout_args()
+        _lib.check(lib.mua_calibrate_multi(*la, hH, nH, int(bool(use_sort)), _WINDOW[window], arr, len(cbs), _stream()))
+    return outs
+
+
+def train_hist_multi(rec: Recording, S_values):
+    """`train_hist` for several alphabet sizes in one pass: {S: int32 [C, S]} (mua_train_hist_multi)."""
+    lib = _lib.load()
+    S_values = [int(S) for S in S_values]
+    assert 1 <= len(S_values) <= 9 and len(set(S_values)) == len(S_values)
+    outs, arr = {}, (_lib.CalibOut * len(S_values))()
+    for i, S in enumerate(S_values):
+        outs[S] = torch.zeros((rec.C, S), dtype=torch.int32, device=rec.device)
+        arr[i].S, arr[i].d_train_hist = S, _addr(outs[S])
+    with torch.cuda.device(rec.device):
+        _lib.check(lib.mua_train_hist_multi(*rec.layout_args(), arr, len(S_values), _stream()))
+    return outs
 
 
 def select_sclv(hist: torch.Tensor, cb: Codebook, active=None, want_min=False):

@@ -113,6 +113,31 @@ int mua_calibrate(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_l
 int mua_train_hist(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
                    int32_t T, int32_t C, int32_t S, int32_t* d_hist_sorted, void* stream);
 
+/* One pass over the recording for SEVERAL alphabet sizes: the reference re-reads and re-saturates every channel for
+ * each S of its sweep (`for S in range(2, 11)`, get_BR_no_sort.py:107 around :140-147 and :171-287); saturation at
+ * S-1 never changes whether a count is >= v for v < S, so one scan with the thresholds of the largest S yields the
+ * windowed histograms of all of them.  h_outs[i] names alphabet size i's table block and output buffers (same
+ * meaning and shapes as the arguments of mua_calibrate / mua_train_hist; NULL outputs are skipped). */
+typedef struct mua_calib_out {
+    int32_t S;
+    const void* d_tables;            /* table block of this S (unused by mua_train_hist_multi) */
+    uint32_t active_lo, active_hi;
+    int32_t* d_cutoff;
+    int32_t* d_end;
+    uint8_t* d_peak;
+    uint8_t* d_enc;
+    int32_t* d_assign_m;
+    int32_t* d_post_m;
+    int64_t* d_bits;
+    int64_t* d_nsym;
+    int32_t* d_train_hist;           /* mua_train_hist_multi only */
+} mua_calib_out;
+int mua_calibrate_multi(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
+                        int32_t T, int32_t C, const int32_t* h_H, int32_t nH, int32_t use_sort,
+                        int32_t window_mode, const mua_calib_out* h_outs, int32_t nS, void* stream);
+int mua_train_hist_multi(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
+                         int32_t T, int32_t C, const mua_calib_out* h_outs, int32_t nS, void* stream);
+
 /* SCLV cost + selection on N histograms int32 [N][S] (np.matmul + np.argmin,
  * get_BR_no_sort.py:229-236): d_enc[n] = first argmin over active rows; optional d_min1/d_min2 =
  * smallest and second-smallest cost (for the elimination score, :307-316). */

@@ -210,3 +210,29 @@ def test_lane_decoder_domain(case):
         assert int(es.total_bits[c]) == total and np.array_equal(es.channel_bytes(c), want)
         got = rec.channel_to_host(c, dec)[st[c]:en[c]]
         assert np.array_equal(got, np.minimum(x[st[c]:en[c]], S - 1))
+
+
+@pytest.mark.parametrize("window,use_sort", [("skip", True), ("truncate", False), ("skip", False)])
+def test_calibrate_multi_equals_per_alphabet(window, use_sort, sclv_tables):
+    """One pass for all alphabet sizes 2..10 (mua_calibrate_multi / mua_train_hist_multi) == nine single-S passes,
+    every output, ragged rows incl. rows shorter than the history lengths and an empty one."""
+    rng = np.random.default_rng(11)
+    chans = [rng.poisson(0.3 + 0.25 * (i % 9), size=int(n)).astype(np.uint8)
+             for i, n in enumerate(list(rng.integers(1, 9000, size=60)) + [3, 17, 1025, 2048, 2049])]
+    chans[7][::5] = 200                                              # counts far above every S-1
+    rec = P.Recording.from_channels(chans, DEV)
+    S_values = list(range(2, 11))
+    cbs = [mua_b200.Codebook(S, sclv_tables[S], device=DEV) for S in S_values]
+    multi = P.calibrate_multi(rec, cbs, O.HIST_SIZES, use_sort=use_sort, window=window)
+    tm = P.train_hist_multi(rec, S_values)
+    for cb in cbs:
+        one = P.calibrate(rec, cb, O.HIST_SIZES, use_sort=use_sort, window=window)
+        for k, v in one.items():
+            assert torch.equal(multi[cb.S][k], v), (cb.S, k)
+        assert torch.equal(tm[cb.S], P.train_hist(rec, cb.S))
+    # a subset of alphabets whose largest is <= 6 takes the narrower scan
+    sub = P.calibrate_multi(rec, [cbs[1], cbs[3]], [64], use_sort=use_sort, window=window)
+    for cb in (cbs[1], cbs[3]):
+        one = P.calibrate(rec, cb, [64], use_sort=use_sort, window=window)
+        for k, v in one.items():
+            assert torch.equal(sub[cb.S][k], v), (cb.S, k)
