@@ -87,9 +87,37 @@ void launch_calibrate(const CalibParams& P, cudaStream_t st) {
     k_calibrate<SS, MULTI><<<grid, CAL_WARPS * 32, 0, st>>>(P);
 }
 
+template <int S>
+void launch_calibrate_head(const CalibParams& P, cudaStream_t st) {
+    if (P.H[0] <= 128) {
+        const long long threads = (long long)P.L.C * 4;
+        k_calibrate_head<S, 4><<<(unsigned)((threads + CALH_THREADS - 1) / CALH_THREADS), CALH_THREADS, 0, st>>>(P);
+    } else {
+        const long long threads = (long long)P.L.C * 32;
+        k_calibrate_head<S, 32><<<(unsigned)((threads + CALH_THREADS - 1) / CALH_THREADS), CALH_THREADS, 0, st>>>(P);
+    }
+}
+
 // one alphabet size: the scan counts exactly its thresholds; several: one scan with the thresholds of the largest
 int dispatch_calibrate(const CalibParams& P, cudaStream_t st) {
     if (P.L.C == 0) return MUA_OK;
+    if (P.nS == 1 && P.nH == 1 && !P.train && !P.need_post && P.H[0] <= 1024) {
+        // calibration window only (the streaming system): a few lanes per channel
+        switch (P.out[0].S) {
+            case 2: launch_calibrate_head<2>(P, st); break;
+            case 3: launch_calibrate_head<3>(P, st); break;
+            case 4: launch_calibrate_head<4>(P, st); break;
+            case 5: launch_calibrate_head<5>(P, st); break;
+            case 6: launch_calibrate_head<6>(P, st); break;
+            case 7: launch_calibrate_head<7>(P, st); break;
+            case 8: launch_calibrate_head<8>(P, st); break;
+            case 9: launch_calibrate_head<9>(P, st); break;
+            case 10: launch_calibrate_head<10>(P, st); break;
+            default: return fail(MUA_E_INVALID, "S=%d outside 2..10", P.out[0].S);
+        }
+        CHECK_LAUNCH("k_calibrate_head");
+        return MUA_OK;
+    }
     if (P.nS == 1) {
         switch (P.out[0].S) {
             case 2: launch_calibrate<2, false>(P, st); break;

@@ -416,6 +416,117 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// calibrate, calibration window only: G lanes per channel
+// ---------------------------------------------------------------------------------------------
+// The streaming system (test_chosen_system.py:80-97, one history length, bit counts taken from the encoder)
+// needs only the first cutoff <= H <= 1024 samples of a channel: cutoff, window end, peak and SCLV row.  A whole
+// warp per channel (k_calibrate) spends ~1000 instructions on those 64 bytes; here G lanes share a channel, each
+// counting #{x >= v} over its 16-byte pieces, the counts meet by xor-shuffles, every lane of the group rebuilds
+// the histogram / peak / rank map, the SCLV rows are dealt round-robin to the lanes and the (cost, row) pairs are
+// min-reduced (lowest cost, then lowest row = np.argmin's first minimum, get_BR_no_sort.py:236).
+constexpr int CALH_THREADS = 128;
+
+template <int S, int G>
+__global__ void __launch_bounds__(CALH_THREADS) k_calibrate_head(const __grid_constant__ CalibParams P) {
+    __shared__ uint4 s_len4[MUA_MAX_K], s_rank4[MUA_MAX_S];
+    const CalOut& O = P.out[0];
+    {
+        const uint4* gl = reinterpret_cast<const uint4*>(&O.tab->lens[0][0]);
+        const uint4* gr = reinterpret_cast<const uint4*>(&O.tab->rank[0][0]);
+        for (int i = threadIdx.x; i < MUA_MAX_K; i += CALH_THREADS) s_len4[i] = gl[i];
+        if (threadIdx.x < MUA_MAX_S) s_rank4[threadIdx.x] = gr[threadIdx.x];
+    }
+    __syncthreads();
+    const uint8_t(*s_len)[16] = reinterpret_cast<const uint8_t(*)[16]>(s_len4);
+    const uint8_t(*s_rank)[16] = reinterpret_cast<const uint8_t(*)[16]>(s_rank4);
+    const int c_raw = (int)(((long long)blockIdx.x * CALH_THREADS + threadIdx.x) / G);
+    const int g = threadIdx.x % G;
+    const bool valid = c_raw < P.L.C;
+    const int c = valid ? c_raw : P.L.C - 1;          // idle groups shadow the last channel (shuffles stay warp-wide)
+    const int n = ch_len(P.L, c);
+    const uint8_t* row = P.L.sym + ch_off(P.L, c);
+    const int cut = n > 0 ? min(max(P.H[0], 1), n) : 0;
+
+    int cnt[S];                                        // cnt[v] = #{t < cut : x_t >= v}
+#pragma unroll
+    for (int v = 0; v < S; ++v) cnt[v] = 0;
+    for (int p0 = g * 16; p0 < cut; p0 += G * 16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row + p0);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const int nvalid = min(16, cut - p0);          // bytes of this piece inside the window: 1..16
+        const int full = nvalid >> 2, part = nvalid & 3;
+        // flag of byte i of word j sits at bit 8i + j: words below `full` count whole, word `full` its first `part` bytes
+        const uint32_t vm = ((1u << full) - 1u) * 0x01010101u | ((1u << full) * (0x01010101u & ((1u << (8 * part)) - 1u)));
+        uint32_t lo7[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lo7[j] = w[j] & 0x7F7F7F7Fu;
+#pragma unroll
+        for (int v = 1; v < S; ++v) {
+            const uint32_t u = (ge_mask(w[0], lo7[0], v) >> 7) | (ge_mask(w[1], lo7[1], v) >> 6) |
+                               (ge_mask(w[2], lo7[2], v) >> 5) | (ge_mask(w[3], lo7[3], v) >> 4);
+            cnt[v] += __popc(u & vm);
+        }
+    }
+#pragma unroll
+    for (int v = 1; v < S; ++v) {
+#pragma unroll
+        for (int d = G / 2; d; d >>= 1) cnt[v] += __shfl_xor_sync(FULL, cnt[v], d);
+    }
+    int hist[S];
+    {
+        int g_prev = cut;                              // G_0 = number of samples
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int g_next = s + 1 < S ? cnt[s + 1] : 0;
+            hist[s] = g_prev - g_next;
+            g_prev = g_next;
+        }
+    }
+    int p = 0;
+    if (P.use_sort) {                                  // np.argmax: lowest index on ties (functions_1.py:77)
+        int best = hist[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s)
+            if (hist[s] > best) { best = hist[s]; p = s; }
+    }
+    int rk[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) rk[s] = s_rank[p][s];
+    const int K = O.tab->K;
+    long long best_cost = 0;
+    int enc = -1;
+    for (int k = g; k < K; k += G) {
+        if (!((O.active >> k) & 1ull)) continue;
+        long long cost = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) cost += (long long)hist[s] * s_len[k][rk[s]];
+        if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
+    }
+#pragma unroll
+    for (int d = G / 2; d; d >>= 1) {
+        const long long oc = __shfl_xor_sync(FULL, best_cost, d);
+        const int ok = __shfl_xor_sync(FULL, enc, d);
+        if (ok >= 0 && (enc < 0 || oc < best_cost || (oc == best_cost && ok < enc))) { best_cost = oc; enc = ok; }
+    }
+    if (!valid || g != 0) return;
+    int end = cut;
+    if (P.mode == MUA_WINDOW_SKIP) {
+        end = cut + n / 2;
+        if (end > n) end = -1;
+    } else if (P.mode == MUA_WINDOW_TRUNCATE) {
+        end = min(cut + n / 2, n);
+    }
+    if (O.cutoff) O.cutoff[c] = cut;
+    if (O.end) O.end[c] = end;
+    if (O.peak) O.peak[c] = (uint8_t)p;
+    if (O.enc) O.enc[c] = (uint8_t)(enc < 0 ? 0 : enc);
+    if (O.assign_m) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) O.assign_m[(size_t)c * S + rk[s]] = hist[s];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // stand-alone selection / bit counts / elimination scores (thread per histogram)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_select(const int32_t* __restrict__ hist, int64_t N, const TabHdr* __restrict__ T,

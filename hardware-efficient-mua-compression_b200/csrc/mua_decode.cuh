@@ -335,7 +335,14 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 //   * the write-out (8 lanes per 128-byte row) uses per-group precomputed row pointers and is fully unrolled.
 constexpr int DL_WARPS = 14;           // launched warps (more do not help: see profiles/r01_summary.md); those with a buffer in the runtime layout work
 constexpr int DL_ROW_B = 144;          // stream ring row: 128 B + 16 B pad
-constexpr int DL_OUT_B = 144;          // output tile row: 128 B + 16 B pad
+#ifndef MUA_DL_OB
+#define MUA_DL_OB 128
+#endif
+#ifndef MUA_DL_BRANCHFREE
+#define MUA_DL_BRANCHFREE 1
+#endif
+constexpr int DL_OBN = MUA_DL_OB / 128;         // 128-symbol periods per write-out
+constexpr int DL_OUT_B = MUA_DL_OB + 16;        // output tile row: 128 or 256 B + 16 B pad (row starts 4 banks apart)
 constexpr int DL_MAX_ROWS = 3;         // codebook rows (K) whose lane-replicated tables fit
 constexpr int DL_TAB_B = 256 * 32 * 4; // one lane-replicated table: 32 KB
 constexpr int DL_PER_WARP = 32 * DL_ROW_B + 32 * DL_OUT_B;
@@ -555,7 +562,8 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
             if (done == 0) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    w0[c] = stream_rev(rowp[c][rp[c]]); w1[c] = stream_rev(rowp[c][rp[c] + 1]); wn[c] = stream_rev(rowp[c][rp[c] + 2]);
+                    w0[c] = stream_rev(rowp[c][rp[c]]); w1[c] = stream_rev(rowp[c][rp[c] + 1]);
+                    wn[c] = MUA_DL_BRANCHFREE ? rowp[c][rp[c] + 2] : stream_rev(rowp[c][rp[c] + 2]);
                     rp[c] += 3;
                 }
             }
@@ -584,8 +592,22 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     off[c] += o[c];
+#if MUA_DL_BRANCHFREE
+                    {   // branch-free refill: the word after next is read every time and kept RAW (it is bit-reversed when it
+                        // moves into w1, a refill later, so nothing ever waits for this load)
+                        const bool rf = off[c] >= 32;
+                        const uint32_t nxt = rowp[c][rp[c] & 31];
+                        const uint32_t w1n = stream_rev(wn[c]);
+                        w0[c] = rf ? w1[c] : w0[c];
+                        w1[c] = rf ? w1n : w1[c];
+                        wn[c] = rf ? nxt : wn[c];
+                        rp[c] += rf ? 1u : 0u;
+                        off[c] -= rf ? 32u : 0u;
+                    }
+#else
                     if (off[c] >= 32) { w0[c] = w1[c]; w1[c] = wn[c]; wn[c] = stream_rev(rowp[c][rp[c] & 31]); ++rp[c]; off[c] -= 32; }
-                    reinterpret_cast<uint4*>(s_out[c] + lane * DL_OUT_B)[q] = make_uint4(ow[c][0], ow[c][1], ow[c][2], ow[c][3]);
+#endif
+                    reinterpret_cast<uint4*>(s_out[c] + lane * DL_OUT_B + (per % DL_OBN) * 128)[q] = make_uint4(ow[c][0], ow[c][1], ow[c][2], ow[c][3]);
                 }
             }
             if (per == nper - 1) {   // every ring of the warp is free: start the next group's chunks before writing this period out
@@ -596,27 +618,42 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
-            __syncwarp();
-            // ---- coalesced write-out: 8 lanes per 128-byte row, 4 rows per pass ----
+            // ---- coalesced write-out every DL_OBN periods: 8 lanes per 128 bytes of a row, 4 rows per pass; with 256-byte
+            //      tile rows a lane stores both halves of its row back to back (256 contiguous bytes per row reach
+            //      the memory system together: the pure-write probe gives 6.1 TB/s for this pattern, 5.1 for 128) ----
+            if (DL_OBN == 1 || (per % DL_OBN) == DL_OBN - 1 || per == nper - 1) {
+                const int wbase = done - (per % DL_OBN) * 128;                                 // symbol offset of tile column 0
+                __syncwarp();
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                uint4 v[8];
+                for (int c = 0; c < NC; ++c) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(s_out[c] + (i * 4 + wrow) * DL_OUT_B + wcol * 16);
+                    for (int ib = 0; ib < 8; ib += 8 / DL_OBN) {
+                        uint4 v[8 / DL_OBN][DL_OBN];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int vr = (int)((wrem[c][i >> 1] >> (16 * (i & 1))) & 0xFFFFu) - 128 - done;   // valid bytes from this lane's column on
-                    uint8_t* d = reinterpret_cast<uint8_t*>(wptr[c][i]) + done;
-                    if (vr >= 16 && ((wal[c] >> i) & 1)) {
-                        *reinterpret_cast<uint4*>(d) = v[i];
-                    } else if (vr > 0) {   // window edge or unaligned first chunk: byte stores
-                        const uint8_t* sp = s_out[c] + (i * 4 + wrow) * DL_OUT_B + wcol * 16;
-                        const int nbyte = min(16, vr);
-                        for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                        for (int i = 0; i < 8 / DL_OBN; ++i)
+#pragma unroll
+                            for (int hf = 0; hf < DL_OBN; ++hf)
+                                v[i][hf] = *reinterpret_cast<const uint4*>(s_out[c] + ((ib + i) * 4 + wrow) * DL_OUT_B + hf * 128 + wcol * 16);
+#pragma unroll
+                        for (int i0 = 0; i0 < 8 / DL_OBN; ++i0) {
+                            const int i = ib + i0;
+#pragma unroll
+                            for (int hf = 0; hf < DL_OBN; ++hf) {
+                                const int vr = (int)((wrem[c][i >> 1] >> (16 * (i & 1))) & 0xFFFFu) - 128 - wbase - hf * 128;   // valid bytes from this lane's column on
+                                uint8_t* d = reinterpret_cast<uint8_t*>(wptr[c][i]) + wbase + hf * 128;
+                                if (vr >= 16 && ((wal[c] >> i) & 1)) {
+                                    *reinterpret_cast<uint4*>(d) = v[i0][hf];
+                                } else if (vr > 0) {   // window edge or unaligned first chunk: byte stores
+                                    const uint8_t* sp = s_out[c] + (i * 4 + wrow) * DL_OUT_B + hf * 128 + wcol * 16;
+                                    const int nbyte = min(16, vr);
+                                    for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                                }
+                            }
+                        }
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
             done += 128;
         }
         g = gn;

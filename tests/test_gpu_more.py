@@ -236,3 +236,39 @@ def test_calibrate_multi_equals_per_alphabet(window, use_sort, sclv_tables):
         one = P.calibrate(rec, cb, [64], use_sort=use_sort, window=window)
         for k, v in one.items():
             assert torch.equal(sub[cb.S][k], v), (cb.S, k)
+
+
+@pytest.mark.parametrize("S", [2, 3, 4, 5, 7, 9, 10])
+def test_calibrate_head_matches_oracle(S, sclv_tables):
+    """One history length and no post-window output takes the calibration-window kernel (k_calibrate_head, 4 or 32
+    lanes per channel): cutoff / window end / peak / SCLV row / mapped calibration histogram against the oracle, for
+    ragged rows (shorter than H too), every window mode, both sort modes and a restricted row set."""
+    rng = np.random.default_rng(100 + S)
+    lens = list(rng.integers(1, 3000, size=150)) + [1, 2, 15, 16, 17, 63, 64, 65, 127, 128, 129, 1023, 1024, 1025]
+    chans = [rng.poisson(0.2 + 0.3 * (i % (S + 2)), size=int(n)).astype(np.uint8) for i, n in enumerate(lens)]
+    chans[3][::3] = 250
+    rec = P.Recording.from_channels(chans, DEV)
+    cb = mua_b200.Codebook(S, sclv_tables[S], device=DEV)
+    want = ("cutoff", "end", "peak", "enc", "assign_m")
+    masks = [None] + ([(cb.all_active >> 1) or 1, cb.all_active & 0x2AAAAAAAAA or 1] if cb.K > 1 else [])
+    for H in (1, 4, 64, 100, 128, 129, 700, 1024):
+        for window, use_sort, active in (("truncate", True, masks[0]), ("skip", False, masks[-1]), ("none", True, masks[len(masks) // 2])):
+            cal = {k: v.cpu().numpy() for k, v in P.calibrate(rec, cb, [H], use_sort=use_sort, window=window, active=active, want=want).items()}
+            rows = [k for k in range(cb.K) if ((cb.all_active if active is None else active) >> k) & 1]
+            for c, x in enumerate(chans):
+                cutoff, end, a, _, skipped = O.window_hists(x, S, H, skip_rule=(window == "skip"))
+                if use_sort:
+                    _, am = O.approx_sort(a)
+                    peak = int(np.argmax(a))
+                else:
+                    am, peak = a, 0
+                enc = rows[int(O.select_sclv(am, sclv_tables[S][rows]))]
+                want_end = cutoff if window == "none" else (-1 if skipped else min(end, len(x)))
+                got = (cal["cutoff"][c, 0], cal["end"][c, 0], cal["peak"][c, 0], cal["enc"][c, 0])
+                assert got == (cutoff, want_end, peak, enc), (S, H, window, c, got, (cutoff, want_end, peak, enc))
+                assert np.array_equal(cal["assign_m"][c, 0], am)
+    # and the same answers as the general kernel (which also scans the post window)
+    full = P.calibrate(rec, cb, [64], use_sort=True, window="truncate")
+    head = P.calibrate(rec, cb, [64], use_sort=True, window="truncate", want=want)
+    for k in want:
+        assert torch.equal(full[k], head[k]), k
