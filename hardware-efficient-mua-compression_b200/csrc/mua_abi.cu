@@ -272,7 +272,7 @@ int mua_calibrate_multi(const uint8_t* d_sym, const int64_t* d_off, const int32_
     CalibParams P;
     memset(&P, 0, sizeof(P));
     P.L = Layout{d_sym, d_off, d_len, stride, T, C};
-    P.nH = nH; P.use_sort = use_sort; P.mode = window_mode; P.train = 0; P.nS = nS;
+    P.nH = nH; P.use_sort = use_sort; P.mode = window_mode; P.train = 0; P.nS = nS; P.one = 1;
     for (int i = 0; i < nH; ++i) P.H[i] = h_H[i];
     for (int i = 0; i < nS; ++i) {
         const mua_calib_out& o = h_outs[i];
@@ -306,7 +306,7 @@ int mua_train_hist_multi(const uint8_t* d_sym, const int64_t* d_off, const int32
     CalibParams P;
     memset(&P, 0, sizeof(P));
     P.L = Layout{d_sym, d_off, d_len, stride, T, C};
-    P.nH = 1; P.use_sort = 0; P.mode = MUA_WINDOW_NONE; P.train = 1; P.nS = nS;
+    P.nH = 1; P.use_sort = 0; P.mode = MUA_WINDOW_NONE; P.train = 1; P.nS = nS; P.one = 1;
     P.H[0] = 0x7FFFFFFF;
     for (int i = 0; i < nS; ++i) {
         REQUIRE(h_outs[i].S >= 2 && h_outs[i].S <= MUA_MAX_S, "S=%d outside 2..10", h_outs[i].S);

@@ -85,6 +85,9 @@ __device__ __forceinline__ int bytesum4(uint32_t x) {
     return (int)((y & 0xFFFFu) + (y >> 16));
 }
 
+// what a lane's packed streaming counter holds, as a count
+__device__ __forceinline__ int cal_flush(uint32_t x);
+
 // ---------------------------------------------------------------------------------------------
 // calibrate: warp per channel
 // ---------------------------------------------------------------------------------------------
@@ -112,10 +115,24 @@ struct CalOut {                 // outputs and tables of one alphabet size
 struct CalibParams {
     Layout L;
     int32_t nH, use_sort, mode, train, nS, need_post;
+    uint32_t one;               // == 1, opaque to ptxas: multiplier of the adds that are to run on the FMA pipe
     int32_t H[MUA_MAX_H];
     CalOut out[CAL_MAX_NS];
 };
 
+#ifndef MUA_CAL_ACC
+#define MUA_CAL_ACC 1          // 0: byte counters on the ALU pipe; 1: IMAD compare-add + DP4A flag sum
+#endif
+#ifndef MUA_CAL_NALU
+#define MUA_CAL_NALU 2         // thresholds whose compare-add stays on the ALU pipe (pipe balance)
+#endif
+__device__ __forceinline__ int cal_flush(uint32_t x) {
+#if MUA_CAL_ACC == 1
+    return (int)(x >> 7);       // DP4A adds 0x80 per flagged byte
+#else
+    return bytesum4(x);         // four byte counters
+#endif
+}
 constexpr int CAL_WARPS = 4;
 constexpr int CAL_TILE = 512;   // bytes per warp step (16 B per lane)
 
@@ -323,7 +340,6 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
         for (int u = 0; u < UNR; ++u) {
             const int ts = t0 + u * CAL_TILE;
             if (ts >= scan_end) break;
-            const int p0 = ts + lane * 16;
             const uint32_t w[4] = {qv[u].x, qv[u].y, qv[u].z, qv[u].w};
             uint32_t lo7[4];
 #pragma unroll
@@ -340,7 +356,7 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
                 uint32_t ex[NPK];
 #pragma unroll
                 for (int v = 1; v < S; ++v) {
-                    base[v] = __reduce_add_sync(FULL, acc[v] + bytesum4(accb[v]));
+                    base[v] = __reduce_add_sync(FULL, acc[v] + cal_flush(accb[v]));
                     u[v] = (ge_mask(w[0], lo7[0], v) >> 7) | (ge_mask(w[1], lo7[1], v) >> 6) | (ge_mask(w[2], lo7[2], v) >> 5) |
                            (ge_mask(w[3], lo7[3], v) >> 4);
                 }
@@ -378,6 +394,7 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
                 }
                 nextb = next_boundary(ts + CAL_TILE);
             }
+#if MUA_CAL_ACC == 0
 #pragma unroll
             for (int v = 1; v < S; ++v) {
                 accb[v] += (ge_mask(w[0], lo7[0], v) >> 7) + (ge_mask(w[1], lo7[1], v) >> 7) +
@@ -388,6 +405,32 @@ __global__ void __launch_bounds__(CAL_WARPS * 32) k_calibrate(const __grid_const
                 for (int v = 1; v < S; ++v) { acc[v] += bytesum4(accb[v]); accb[v] = 0; }
                 since_flush = 0;
             }
+#else
+            // With byte counters the loop is bound by the ALU pipe (per word and threshold VIADD, LOP3, SHF, IADD, all
+            // issued every other cycle per scheduler) while the FMA pipe idles.  Here the compare-add t = lo7 * 1 + c
+            // is an IMAD (the multiplier is a kernel parameter ptxas cannot fold) and the four flag bytes of a word
+            // are summed into a 32-bit counter by one DP4A (0x80 per flag; no shift, no overflow flushes): per word
+            // and threshold ONE ALU op (LOP3: (t | w) & 0x80808080).  MUA_CAL_NALU thresholds keep their compare-add
+            // on the ALU pipe.  Measured (100k channels x 120k bins, nine history lengths, 6.1 GB scanned): S=5
+            // 1.62 -> 1.01 ms, S=7 2.26 -> 1.35, S=10 3.34 -> 1.97; IMAD.HI (x * 2^25 >> 32) instead of DP4A is slower.
+#pragma unroll
+            for (int v = 1; v < S; ++v) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t t;
+                    const uint32_t cv = (uint32_t)(0x80 - v) * 0x01010101u;
+                    if (v <= MUA_CAL_NALU) t = lo7[j] + cv;
+                    else asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo7[j]), "r"(P.one), "r"(cv));
+                    const uint32_t m = (t | w[j]) & 0x80808080u;
+                    asm("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(accb[v]) : "r"(m), "r"(0x01010101u));
+                }
+            }
+            if (++since_flush == (1 << 19)) {   // 2048 per step at most: a 32-bit counter lasts 2^21 steps
+#pragma unroll
+                for (int v = 1; v < S; ++v) { acc[v] += cal_flush(accb[v]); accb[v] = 0; }
+                since_flush = 0;
+            }
+#endif
         }
     }
     __syncwarp();
