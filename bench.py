@@ -229,12 +229,27 @@ def run_b200(a):
         return rep
 
     sampler = ClockSampler(local) if rank == 0 else None
-    t_w = time.perf_counter()
     nw = 0
-    while nw < max(a.warmup, 3) or (time.perf_counter() - t_w < 1.0 and nw < 600):   # >= 3 warm-up steps, >= 1 s under load
+    for _ in range(max(a.warmup, 3)):                     # >= 3 warm-up steps (the first one also sets NCCL up) ...
         step()
         nw += 1
-        if nw % 8 == 0:
+    torch.cuda.synchronize()
+    # ... then ~1 s under load so that the clock sampler sees it.  Every step of an N > 1 run holds a collective, so
+    # the number of extra steps must be the same on all ranks: sized from three timed steps, MAX over ranks.
+    t_w = time.perf_counter()
+    for _ in range(3):
+        step()
+        nw += 1
+    torch.cuda.synchronize()
+    n_extra = int(min(1000, max(0, 1.0 / max((time.perf_counter() - t_w) / 3, 1e-5))))
+    if world > 1:
+        ne = torch.tensor([n_extra], dtype=torch.int64, device=dev)
+        dist.all_reduce(ne, op=dist.ReduceOp.MAX)
+        n_extra = int(ne.item())
+    for i in range(n_extra):
+        step()
+        nw += 1
+        if i % 8 == 7:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     if world > 1:
