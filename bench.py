@@ -187,6 +187,7 @@ def run_b200(a):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = D.bind_to_gpu_numa_node(local)          # host buffers of this rank on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     C, T = a.channels, a.bins
@@ -341,7 +342,7 @@ def run_b200(a):
                        "l2": "inputs (%.1f GB per GPU) are larger than L2" % (C * T / 1e9), "sharding": "channels, contiguous blocks"},
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * a.steps,
             "clocks": clocks, "BR_bits_per_s_per_channel": float(br["BR"]), "lossless": True,
-            "symbols_per_step": nsym_all}))
+            "symbols_per_step": nsym_all, "numa_node_rank0": numa_node}))
     if world > 1:
         dist.destroy_process_group()
 

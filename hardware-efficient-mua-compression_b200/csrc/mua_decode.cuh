@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 //     128-symbol period ahead of its use; the next group's first bytes are requested before the last period of
 //     the current group is written out;
 //   * the write-out (8 lanes per 128-byte row) uses per-group precomputed row pointers and is fully unrolled.
-constexpr int DL_WARPS = 14;           // launched warps (more do not help: see profiles/r01_summary.md); those with a buffer in the runtime layout work
+#ifndef MUA_DL_WARPS
+#define MUA_DL_WARPS 14        // 8: 1.67 ms, 10: 1.45, 12: 1.32, 14: 1.20, 16: 1.22, 18: 1.27 (96 registers, spills), 20: 1.35
+#endif
+constexpr int DL_WARPS = MUA_DL_WARPS;           // launched warps (more do not help: see profiles/r01_summary.md); those with a buffer in the runtime layout work
 constexpr int DL_ROW_B = 144;          // stream ring row: 128 B + 16 B pad
 #ifndef MUA_DL_OB
 #define MUA_DL_OB 128

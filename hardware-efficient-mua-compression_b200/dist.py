@@ -5,9 +5,45 @@ rank runs the whole pipeline on a contiguous block of channels with no data-path
 per-channel report (bit count, symbol count, chosen SCLV, peak) is gathered -- one all_gather of a
 packed int64 [n, 4] tensor over NCCL/NVLink (gloo on CPU in the tests).  BR float math is done on the
 host over the gathered array in global channel order (np.mean is order sensitive)."""
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node and
+    the node's cpulist), so that the pinned host buffers it allocates afterwards are node-local (first touch) and
+    the host->device copies of one rank do not cross the socket interconnect.  One process per GPU makes this
+    safe; returns the node id, or None when the topology is not exposed (containers often report -1)."""
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return node if cpus else None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None
 
 
 def shard_range(C, rank, world):

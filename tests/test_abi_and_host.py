@@ -125,3 +125,15 @@ def test_sclv_generator_reproduces_reference_tables():
         assert np.array_equal(mua_b200.generator_codes(S), np.array([[int(c, 2) for c in b] for b in books]))
     assert sclv_gen.generate(5)[1] == O.GENERATOR_CODEBOOK_S5
     assert sclv_gen.generate(3)[1] == [["1", "00", "01"]]
+
+
+def test_numa_binding_helpers():
+    """sysfs cpulist parsing; without a GPU (or without an exposed topology) the binding is a no-op."""
+    from mua_b200 import dist as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert D._parse_cpulist("5") == {5}
+    import os
+    before = os.sched_getaffinity(0)
+    node = D.bind_to_gpu_numa_node(0)
+    assert node is None or isinstance(node, int)
+    assert os.sched_getaffinity(0) <= before
