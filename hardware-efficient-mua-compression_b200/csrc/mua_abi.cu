@@ -49,9 +49,9 @@ int sm_count() {
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int check_layout(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C) {
-    REQUIRE(d_sym != nullptr, "d_sym is NULL");
-    REQUIRE(aligned16(d_sym), "d_sym must be 16-byte aligned");
     REQUIRE(C >= 0, "C < 0");
+    REQUIRE(d_sym != nullptr || C == 0, "d_sym is NULL");      // a recording without channels has no buffer
+    REQUIRE(aligned16(d_sym), "d_sym must be 16-byte aligned");
     REQUIRE(T >= 0 && T <= (1 << 28), "T out of range [0, 2^28]");
     if (!d_off) REQUIRE(stride % 16 == 0 && stride >= (int64_t)((T + 15) & ~15), "stride must be a multiple of 16 and >= round_up(T,16)");
     (void)d_len;
@@ -243,7 +243,12 @@ int mua_bin_raster(const void* d_raster, int dtype, int64_t T0, int32_t C, int32
         REQUIRE(nb <= (int64_t)65535 * BIN_TB, "too many bins for one launch");
         dim3 grid((C + BIN_TC - 1) / BIN_TC, (unsigned)((nb + BIN_TB - 1) / BIN_TB));
         REQUIRE(aligned16(d_sym) || sym_stride % 16 != 0, "d_sym must be 16-byte aligned when sym_stride is a multiple of 16");
-        k_bin_sym<<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_sym, sym_stride, S ? S - 1 : 255);
+        if (C % 8 == 0 && bin_res <= 128 && (reinterpret_cast<uintptr_t>(d_raster) & 7) == 0 && nb <= (int64_t)65535 * BW_TB) {
+            dim3 gridw((C + BW_TC - 1) / BW_TC, (unsigned)((nb + BW_TB - 1) / BW_TB));
+            k_bin_sym_wide<<<gridw, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_sym, sym_stride, S ? S - 1 : 255);
+        } else {
+            k_bin_sym<<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_sym, sym_stride, S ? S - 1 : 255);
+        }
         CHECK_LAUNCH("k_bin_sym");
     }
     return MUA_OK;
@@ -310,7 +315,7 @@ int mua_train_hist_multi(const uint8_t* d_sym, const int64_t* d_off, const int32
     P.H[0] = 0x7FFFFFFF;
     for (int i = 0; i < nS; ++i) {
         REQUIRE(h_outs[i].S >= 2 && h_outs[i].S <= MUA_MAX_S, "S=%d outside 2..10", h_outs[i].S);
-        REQUIRE(h_outs[i].d_train_hist, "d_train_hist is NULL");
+        REQUIRE(h_outs[i].d_train_hist || C == 0, "d_train_hist is NULL");
         P.out[i].S = h_outs[i].S;
         P.out[i].active = 1;
         P.out[i].train_hist = h_outs[i].d_train_hist;
@@ -364,6 +369,7 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
                int64_t* d_total_bits, int32_t* d_overflow, void* stream) {
     int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
     if (rc) return rc;
+    if (C == 0) return MUA_OK;                                  // nothing to encode: per-channel arrays may be empty (NULL)
     REQUIRE(d_start && d_end && d_peak && d_enc && d_tables && d_stream && d_chunk_off && d_total_bits && d_overflow, "NULL argument");
     REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
     REQUIRE(chunk_stride >= (T + TILE - 1) / TILE && chunk_stride >= 1, "chunk_stride < ceil(T/%d)", TILE);
@@ -427,6 +433,8 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off, int32_t chunk_stride, const int64_t* d_off,
                int64_t stride, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
                const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end, uint8_t* d_dec, void* stream) {
+    REQUIRE(C >= 0, "C < 0");
+    if (C == 0) return MUA_OK;                                  // nothing to decode: per-channel arrays may be empty (NULL)
     REQUIRE(d_stream && d_chunk_off && d_start && d_end && d_peak && d_enc && d_tables && d_dec, "NULL argument");
     REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
     REQUIRE(aligned16(d_dec), "d_dec must be 16-byte aligned");

@@ -779,4 +779,77 @@ __global__ void __launch_bounds__(256) k_bin_sym(const uint8_t* __restrict__ ras
     }
 }
 
+// Wide variant for C % 8 == 0 and bin_res <= 128 (every bin period of the scripts on a 1 ms raster): tile = 256
+// channels x 64 bins.  A warp sums one bin at a time: 8-byte coalesced loads along channels (lane = 8 channels),
+// four rows in flight, SWAR accumulation in 16-bit lanes (even / odd bytes of a word: 2 LOP + 1 SHF + 2 ADD per
+// 4 raster bytes; 128 rows x 255 < 2^15 keeps the saturation compare carry-free), SWAR min(x, sat), even | odd << 8
+// = four saturated bytes in channel order, one conflict-free 8-byte store into the [bin][channel] tile.  The
+// transpose happens on the read side: thread = channel, 64 byte loads down its column (a warp reads 32 consecutive
+// channels of one tile row: 8 words, broadcast, no conflicts), packed into four 16-byte stores along bins.
+constexpr int BW_TC = 256, BW_TB = 64;
+__global__ void __launch_bounds__(256) k_bin_sym_wide(const uint8_t* __restrict__ raster, int64_t T0, int C, int r, int64_t nb,
+                                                      uint8_t* __restrict__ sym, int64_t stride, int sat) {
+    __shared__ __align__(16) uint8_t tile[BW_TB][BW_TC];
+    const int c0 = blockIdx.x * BW_TC;
+    const int64_t b0 = (int64_t)blockIdx.y * BW_TB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = c0 + 8 * lane;
+    const uint32_t satv = (uint32_t)sat * 0x00010001u, satk = (uint32_t)(0x7FFF - sat) * 0x00010001u;
+    for (int i = 0; i < BW_TB / 8; ++i) {
+        const int bl = warp + 8 * i;
+        const int64_t b = b0 + bl;
+        uint32_t ev[2] = {0, 0}, od[2] = {0, 0};
+        if (b < nb && c < C) {
+            const int64_t r0 = b * r, r1 = min(r0 + (int64_t)r, T0);
+            const uint8_t* p = raster + r0 * C + c;
+            int64_t t = r0;
+            for (; t + 4 <= r1; t += 4, p += 4 * (int64_t)C) {
+                uint2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint2*>(p + u * (int64_t)C);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ev[0] += v[u].x & 0x00FF00FFu; od[0] += (v[u].x >> 8) & 0x00FF00FFu;
+                    ev[1] += v[u].y & 0x00FF00FFu; od[1] += (v[u].y >> 8) & 0x00FF00FFu;
+                }
+            }
+            for (; t < r1; ++t, p += C) {
+                const uint2 v = *reinterpret_cast<const uint2*>(p);
+                ev[0] += v.x & 0x00FF00FFu; od[0] += (v.x >> 8) & 0x00FF00FFu;
+                ev[1] += v.y & 0x00FF00FFu; od[1] += (v.y >> 8) & 0x00FF00FFu;
+            }
+        }
+        uint32_t w[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            // 16-bit lanes: bit 15 of x + (0x7FFF - sat) is set  <=>  x > sat
+            const uint32_t me = (((ev[j] + satk) >> 15) & 0x00010001u) * 0xFFFFu;
+            const uint32_t mo = (((od[j] + satk) >> 15) & 0x00010001u) * 0xFFFFu;
+            const uint32_t e = (ev[j] & ~me) | (satv & me), o = (od[j] & ~mo) | (satv & mo);
+            w[j] = e | (o << 8);
+        }
+        *reinterpret_cast<uint2*>(&tile[bl][8 * lane]) = make_uint2(w[0], w[1]);
+    }
+    __syncthreads();
+    const int cc = c0 + threadIdx.x;
+    if (cc >= C) return;
+    uint8_t* dst = sym + (int64_t)cc * stride + b0;
+    const bool vec = (stride % 16 == 0) && b0 + BW_TB <= nb && ((reinterpret_cast<uintptr_t>(sym) & 15) == 0);
+#pragma unroll
+    for (int q = 0; q < BW_TB / 16; ++q) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 16 * q + 4 * j;
+            o[j] = (uint32_t)tile[k][threadIdx.x] | ((uint32_t)tile[k + 1][threadIdx.x] << 8) |
+                   ((uint32_t)tile[k + 2][threadIdx.x] << 16) | ((uint32_t)tile[k + 3][threadIdx.x] << 24);
+        }
+        if (vec) {
+            reinterpret_cast<uint4*>(dst)[q] = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            for (int k = 0; k < 16 && b0 + 16 * q + k < nb; ++k) dst[16 * q + k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
 }  // namespace mua

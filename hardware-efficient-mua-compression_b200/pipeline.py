@@ -321,7 +321,9 @@ def bin_raster(raster: torch.Tensor, bin_res: int, S: Optional[int] = None, coun
             _lib.check(lib.mua_bin_raster(_ptr(raster), _DT[raster.dtype], T0, Cn, int(bin_res), _ptr(out), None, 0, 0, _stream()))
             return out
         stride = max(_round16(nb), 16)
-        sym = torch.zeros((Cn, stride), dtype=torch.uint8, device=raster.device)
+        sym = torch.empty((Cn, stride), dtype=torch.uint8, device=raster.device)   # every bin is written; only the row padding needs zeros
+        if stride > nb:
+            sym[:, nb:].zero_()
         _lib.check(lib.mua_bin_raster(_ptr(raster), _DT[raster.dtype], T0, Cn, int(bin_res), None, _ptr(sym), stride,
                                       int(S or 0), _stream()))
         return Recording(sym=sym, C=int(Cn), T=int(nb), stride=int(stride))

@@ -272,3 +272,38 @@ def test_calibrate_head_matches_oracle(S, sclv_tables):
     head = P.calibrate(rec, cb, [64], use_sort=True, window="truncate", want=want)
     for k in want:
         assert torch.equal(full[k], head[k]), k
+
+
+def test_degenerate_recordings():
+    """Empty channels, one-sample channels, a recording without channels, windows of 0/1 symbols: nothing crashes,
+    empty inputs give empty outputs, everything else matches the oracle (streams included)."""
+    S, H = 3, 64
+    cb = mua_b200.Codebook(S, np.array([[1, 2, 2]]), device=DEV)
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 2, 3, 15, 16, 17, 0, 63, 64, 65, 66, 127, 129, 1023, 1024, 1025, 2050, 0]
+    chans = [rng.poisson(0.6, size=n).astype(np.uint8) for n in lens]
+    rec = P.Recording.from_channels(chans, DEV)
+    for want in (("cutoff", "end", "peak", "enc"), ("cutoff", "end", "peak", "enc", "bits", "nsym")):   # head / general kernel
+        cal = P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=want)
+        st, en, pk, ec = (cal[k][:, 0].contiguous() for k in ("cutoff", "end", "peak", "enc"))
+        es = P.encode(rec, cb, st, en, pk, ec)
+        dec = P.decode(es, rec, cb, st, en, pk, ec)
+        assert int(es.overflow.item()) == 0 and int(P.verify(rec, dec, S, st, en).item()) == 0
+        for c, x in enumerate(chans):
+            if len(x) == 0:
+                assert int(st[c]) == 0 and int(en[c]) == 0 and int(es.total_bits[c]) == 0
+                continue
+            cutoff, end, a, p, _ = O.window_hists(x, S, H, skip_rule=False)
+            assert (int(st[c]), int(en[c]), int(pk[c])) == (cutoff, min(end, len(x)), int(np.argmax(a)))
+            wantb, total, _ = O.encode_channel(x, cutoff, min(end, len(x)), S, O.rank_of_symbol(int(np.argmax(a)), S), cb.codes[0], cb.lens[0])
+            assert int(es.total_bits[c]) == total and np.array_equal(es.channel_bytes(c), wantb)
+            if "bits" in cal:
+                assert int(cal["bits"][c, 0]) == total
+    # no channels at all
+    empty = P.Recording.from_matrix(np.zeros((0, 32), dtype=np.uint8), DEV)
+    cal0 = P.calibrate(empty, cb, [H], use_sort=True, window="truncate")
+    assert cal0["cutoff"].shape == (0, 1)
+    z = torch.zeros(0, dtype=torch.int32, device=DEV)
+    es0 = P.encode(empty, cb, z, z, z.to(torch.uint8), z.to(torch.uint8))
+    assert es0.total_bits.numel() == 0 and int(es0.overflow.item()) == 0
+    assert P.train_hist(empty, S).shape == (0, S)
