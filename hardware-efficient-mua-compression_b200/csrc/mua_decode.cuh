@@ -338,14 +338,13 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 #endif
 constexpr int DL_WARPS = MUA_DL_WARPS;           // launched warps (more do not help: see profiles/r01_summary.md); those with a buffer in the runtime layout work
 constexpr int DL_ROW_B = 144;          // stream ring row: 128 B + 16 B pad
-#ifndef MUA_DL_OB
-#define MUA_DL_OB 128
-#endif
 #ifndef MUA_DL_BRANCHFREE
 #define MUA_DL_BRANCHFREE 1
 #endif
-constexpr int DL_OBN = MUA_DL_OB / 128;         // 128-symbol periods per write-out
-constexpr int DL_OUT_B = MUA_DL_OB + 16;        // output tile row: 128 or 256 B + 16 B pad (row starts 4 banks apart)
+#ifndef MUA_DL_FASTWO
+#define MUA_DL_FASTWO 1
+#endif
+constexpr int DL_OUT_B = 144;          // output tile row: 128 B + 16 B pad (row starts 4 banks apart)
 constexpr int DL_MAX_ROWS = 3;         // codebook rows (K) whose lane-replicated tables fit
 constexpr int DL_TAB_B = 256 * 32 * 4; // one lane-replicated table: 32 KB
 constexpr int DL_PER_WARP = 32 * DL_ROW_B + 32 * DL_OUT_B;
@@ -424,6 +423,8 @@ struct DecRing {
     uint32_t wp;              // bytes issued so far, from the origin (multiple of 32)
 };
 
+// decoded-symbol store (st.global.cs / .wt instead of the default write-back operator: no difference, 1.204 / 1.207 / 1.210 ms)
+__device__ __forceinline__ void st_out16(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 __device__ __forceinline__ void cp_async16(uint32_t dst, unsigned long long src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -515,10 +516,12 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
         const long long nlim = gn < ngroups ? nitems : 0;
         uint32_t lbase[NC], mlo[NC], mhi[NC], rp[NC], off[NC], w0[NC], w1[NC], wn[NC];
         int rem[NC];
-        // write-out roles: in pass i this lane stores 16 bytes of row 4i + wrow of every chain's tile
+        // write-out roles: in pass i this lane stores 16 bytes of row 4i + wrow of every chain's tile.  Per group and pass
+        // the lane knows for how many periods that store is a complete, aligned 16-byte store (nibble i of wnf); the
+        // periods in which any lane of the warp has something else to store (a window edge inside its 16 bytes, an
+        // unaligned first chunk) are flagged warp-wide in wslow and take the general path.
         unsigned long long wptr[NC][8];
-        uint32_t wrem[NC][4];                                                         // valid bytes from this lane's column on, + 128, two per register
-        uint32_t wal[NC];
+        uint32_t wnf[NC], wslow[NC];
         int maxrem = 0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -526,15 +529,22 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mlo[c]), "=r"(mhi[c]) : "r"(map_a + cur[c].pk * 8));
             rem[c] = cur[c].rem;
             maxrem = max(maxrem, rem[c]);
-            wal[c] = 0;
+            wnf[c] = 0;
+            uint32_t slow = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = i * 4 + wrow;
                 wptr[c][i] = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(cur[c].optr), r) + wcol * 16;
-                const uint32_t wr = (uint32_t)(__shfl_sync(FULL, rem[c], r) - wcol * 16 + 128);
-                wrem[c][i >> 1] = (i & 1) ? (wrem[c][i >> 1] | (wr << 16)) : wr;
-                wal[c] |= ((wptr[c][i] & 15) == 0 ? 1u : 0u) << i;
+                const int R = __shfl_sync(FULL, rem[c], r) - wcol * 16;              // valid bytes from this lane's column on
+                if ((wptr[c][i] & 15) == 0) {
+                    const int nf = R >= 16 ? ((R - 16) >> 7) + 1 : 0;                 // periods p with R - 128 p >= 16
+                    wnf[c] |= (uint32_t)nf << (4 * i);
+                    if (R - 128 * nf > 0) slow |= 1u << nf;                           // 1..15 bytes left in the period after
+                } else if (R > 0) {
+                    slow |= (1u << ((R + 127) >> 7)) - 1u;                            // unaligned row: byte stores throughout
+                }
             }
+            wslow[c] = MUA_DL_FASTWO ? __reduce_or_sync(FULL, slow) : 0xFFFFFFFFu;
             // position of the chunk's first bit in the ring frame
             const uint32_t boff =
                 (uint32_t)(reinterpret_cast<unsigned long long>(cur[c].sbase) + (cur[c].bp >> 3) - R[c].org) * 8 + (cur[c].bp & 7);
@@ -610,7 +620,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
 #else
                     if (off[c] >= 32) { w0[c] = w1[c]; w1[c] = wn[c]; wn[c] = stream_rev(rowp[c][rp[c] & 31]); ++rp[c]; off[c] -= 32; }
 #endif
-                    reinterpret_cast<uint4*>(s_out[c] + lane * DL_OUT_B + (per % DL_OBN) * 128)[q] = make_uint4(ow[c][0], ow[c][1], ow[c][2], ow[c][3]);
+                    reinterpret_cast<uint4*>(s_out[c] + lane * DL_OUT_B)[q] = make_uint4(ow[c][0], ow[c][1], ow[c][2], ow[c][3]);
                 }
             }
             if (per == nper - 1) {   // every ring of the warp is free: start the next group's chunks before writing this period out
@@ -621,42 +631,34 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
-            // ---- coalesced write-out every DL_OBN periods: 8 lanes per 128 bytes of a row, 4 rows per pass; with 256-byte
-            //      tile rows a lane stores both halves of its row back to back (256 contiguous bytes per row reach
-            //      the memory system together: the pure-write probe gives 6.1 TB/s for this pattern, 5.1 for 128) ----
-            if (DL_OBN == 1 || (per % DL_OBN) == DL_OBN - 1 || per == nper - 1) {
-                const int wbase = done - (per % DL_OBN) * 128;                                 // symbol offset of tile column 0
-                __syncwarp();
+            // ---- coalesced write-out: 8 lanes per 128-byte row, 4 rows per pass ----
+            __syncwarp();
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
+            for (int c = 0; c < NC; ++c) {
+                uint4 v[8];
 #pragma unroll
-                    for (int ib = 0; ib < 8; ib += 8 / DL_OBN) {
-                        uint4 v[8 / DL_OBN][DL_OBN];
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(s_out[c] + (i * 4 + wrow) * DL_OUT_B + wcol * 16);
+                if (!((wslow[c] >> per) & 1u)) {   // warp-uniform: every store of this period is a complete aligned 16-byte store or nothing
 #pragma unroll
-                        for (int i = 0; i < 8 / DL_OBN; ++i)
+                    for (int i = 0; i < 8; ++i)
+                        if ((uint32_t)per < ((wnf[c] >> (4 * i)) & 15u)) st_out16(reinterpret_cast<uint8_t*>(wptr[c][i]) + done, v[i]);
+                } else {
 #pragma unroll
-                            for (int hf = 0; hf < DL_OBN; ++hf)
-                                v[i][hf] = *reinterpret_cast<const uint4*>(s_out[c] + ((ib + i) * 4 + wrow) * DL_OUT_B + hf * 128 + wcol * 16);
-#pragma unroll
-                        for (int i0 = 0; i0 < 8 / DL_OBN; ++i0) {
-                            const int i = ib + i0;
-#pragma unroll
-                            for (int hf = 0; hf < DL_OBN; ++hf) {
-                                const int vr = (int)((wrem[c][i >> 1] >> (16 * (i & 1))) & 0xFFFFu) - 128 - wbase - hf * 128;   // valid bytes from this lane's column on
-                                uint8_t* d = reinterpret_cast<uint8_t*>(wptr[c][i]) + wbase + hf * 128;
-                                if (vr >= 16 && ((wal[c] >> i) & 1)) {
-                                    *reinterpret_cast<uint4*>(d) = v[i0][hf];
-                                } else if (vr > 0) {   // window edge or unaligned first chunk: byte stores
-                                    const uint8_t* sp = s_out[c] + (i * 4 + wrow) * DL_OUT_B + hf * 128 + wcol * 16;
-                                    const int nbyte = min(16, vr);
-                                    for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
-                                }
-                            }
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + wrow;
+                        const int vr = __shfl_sync(FULL, rem[c], r) - wcol * 16 - done;   // valid bytes from this lane's column on
+                        uint8_t* d = reinterpret_cast<uint8_t*>(wptr[c][i]) + done;
+                        if (vr >= 16 && (wptr[c][i] & 15) == 0) {
+                            *reinterpret_cast<uint4*>(d) = v[i];
+                        } else if (vr > 0) {   // window edge or unaligned first chunk: byte stores
+                            const uint8_t* sp = s_out[c] + r * DL_OUT_B + wcol * 16;
+                            const int nbyte = min(16, vr);
+                            for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
                         }
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
             done += 128;
         }
         g = gn;
