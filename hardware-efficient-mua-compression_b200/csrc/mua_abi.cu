@@ -227,7 +227,14 @@ int mua_bin_raster(const void* d_raster, int dtype, int64_t T0, int32_t C, int32
     if (d_counts) {
         dim3 grid((C + 255) / 256, (unsigned)(nb < 32768 ? nb : 32768));
         switch (dtype) {
-            case MUA_DT_U8: k_bin_counts<uint8_t, unsigned long long><<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_counts); break;
+            case MUA_DT_U8:
+                if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(d_raster) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_counts) & 15) == 0) {
+                    dim3 grid4((C / 4 + 255) / 256, (unsigned)(nb < 32768 ? nb : 32768));
+                    k_bin_counts_u8x4<<<grid4, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_counts);
+                } else {
+                    k_bin_counts<uint8_t, unsigned long long><<<grid, 256, 0, st>>>((const uint8_t*)d_raster, T0, C, bin_res, nb, d_counts);
+                }
+                break;
             case MUA_DT_I32: k_bin_counts<int32_t, long long><<<grid, 256, 0, st>>>((const int32_t*)d_raster, T0, C, bin_res, nb, d_counts); break;
             case MUA_DT_I64: k_bin_counts<int64_t, long long><<<grid, 256, 0, st>>>((const int64_t*)d_raster, T0, C, bin_res, nb, d_counts); break;
             case MUA_DT_F32: k_bin_counts<float, float><<<grid, 256, 0, st>>>((const float*)d_raster, T0, C, bin_res, nb, d_counts); break;

@@ -317,7 +317,7 @@ def bin_raster(raster: torch.Tensor, bin_res: int, S: Optional[int] = None, coun
     nb = (T0 + bin_res - 1) // bin_res
     with torch.cuda.device(raster.device):
         if counts:
-            out = torch.zeros((nb, Cn), dtype=torch.int64, device=raster.device)
+            out = torch.empty((nb, Cn), dtype=torch.int64, device=raster.device)      # every (bin, channel) is written
             _lib.check(lib.mua_bin_raster(_ptr(raster), _DT[raster.dtype], T0, Cn, int(bin_res), _ptr(out), None, 0, 0, _stream()))
             return out
         stride = max(_round16(nb), 16)

@@ -63,15 +63,17 @@ def test_bin_raster_symbols():
     rng = np.random.default_rng(3)
     # C % 8 == 0 and bin_res <= 128 take the wide kernel (k_bin_sym_wide), everything else the general one
     for (T0, C, r, S) in [(1000, 96, 50, 3), (999, 130, 7, 5), (4097, 33, 1, 10), (70, 4, 100, 2), (5000, 256, 1, 3),
-                          (3001, 264, 5, 4), (2600, 512, 128, 10), (2600, 512, 129, 10), (100, 8, 3, 3), (6500, 40, 20, 7)]:
+                          (3001, 264, 5, 4), (2600, 512, 128, 10), (2600, 512, 129, 10), (100, 8, 3, 3), (6500, 40, 20, 7), (2000, 12, 700, 3)]:
         raster = rng.poisson(0.05 * r / max(r, 1) + 0.3, size=(T0, C)).astype(np.uint8)
         raster[rng.integers(0, T0, size=40), rng.integers(0, C, size=40)] = 255      # bins far above saturation
-        if r == 128:
-            raster[:128, :9] = 255                                                   # the largest sum a 16-bit lane must hold
+        if r >= 128:
+            raster[:r, :9] = 255                                                   # the largest sum a 16-bit lane must hold
         want = np.minimum(O.bin_mua_data(raster, r), S - 1).T            # [C, nb]
         rec = P.bin_raster(torch.from_numpy(raster).to(DEV), r, S=S, counts=False)
         got = _cpu(rec.sym)[:, :rec.T]
         assert rec.T == want.shape[1] and np.array_equal(got, want)
+        cnt = P.bin_raster(torch.from_numpy(raster).to(DEV), r, counts=True)          # the literal bin_MUA_data output
+        assert cnt.dtype == torch.int64 and np.array_equal(_cpu(cnt), O.bin_mua_data(raster, r))
         if C in (96, 256):                                               # unsaturated symbols (clamped to uint8)
             rec = P.bin_raster(torch.from_numpy(raster).to(DEV), r, S=None, counts=False)
             assert np.array_equal(_cpu(rec.sym)[:, :rec.T], np.minimum(O.bin_mua_data(raster, r), 255).T)
