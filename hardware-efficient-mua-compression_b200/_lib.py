@@ -29,6 +29,7 @@ SIGNATURES = {
     "mua_tables_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mua_build_tables": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "mua_bin_raster": (C.c_int, [_vp, C.c_int, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "mua_bin_events": (C.c_int, [_vp, _vp, _i64, C.c_double, C.c_double, _i64, _i32, _vp, _i64, _i32, _vp]),
     "mua_calibrate": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _u32, _u32,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mua_train_hist": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),

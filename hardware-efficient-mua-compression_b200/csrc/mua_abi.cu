@@ -261,6 +261,27 @@ int mua_bin_raster(const void* d_raster, int dtype, int64_t T0, int32_t C, int32
     return MUA_OK;
 }
 
+int mua_bin_events(const double* d_times, const int32_t* d_chan, int64_t N, double t0, double w, int64_t nb, int32_t C,
+                   uint8_t* d_sym, int64_t sym_stride, int32_t S, void* stream) {
+    REQUIRE(N >= 0 && nb >= 0 && C >= 0, "bad N/nb/C");
+    REQUIRE(w > 0.0 && t0 == t0, "bin width must be positive and t0 a number");
+    REQUIRE(S == 0 || (S >= 2 && S <= MUA_MAX_S), "S outside {0, 2..10}");
+    if (nb == 0 || C == 0) return MUA_OK;
+    REQUIRE(d_sym, "d_sym is NULL");
+    REQUIRE(sym_stride >= nb && sym_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(d_sym) & 3) == 0,
+            "sym_stride must be >= nb and a multiple of 4, d_sym 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_sym, 0, (size_t)C * (size_t)sym_stride, st);
+    if (e != cudaSuccess) return cuda_fail(e, "zero the symbol buffer");
+    if (N == 0) return MUA_OK;
+    REQUIRE(d_times && d_chan, "NULL argument");
+    const long long blocks = (N + 255) / 256, cap = (long long)sm_count() * 16;
+    k_bin_events<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(d_times, d_chan, N, t0, w, nb, C, d_sym, sym_stride,
+                                                                      S ? (uint32_t)(S - 1) : 255u);
+    CHECK_LAUNCH("k_bin_events");
+    return MUA_OK;
+}
+
 int mua_calibrate(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C, int32_t S,
                   const int32_t* h_H, int32_t nH, int32_t use_sort, int32_t window_mode, const void* d_tables, uint32_t active_lo,
                   uint32_t active_hi, int32_t* d_cutoff, int32_t* d_end, uint8_t* d_peak, uint8_t* d_enc, int32_t* d_assign_m,

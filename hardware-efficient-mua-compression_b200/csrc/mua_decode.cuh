@@ -332,18 +332,14 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 //   * the stream reaches each lane through a 128-byte ring that is topped up with cp.async (LDGSTS) one
 //     128-symbol period ahead of its use; the next group's first bytes are requested before the last period of
 //     the current group is written out;
-//   * the write-out (8 lanes per 128-byte row) uses per-group precomputed row pointers and is fully unrolled.
+//   * the write-out (8 lanes per 128-byte row) uses per-group precomputed row pointers and store counts (for how many
+//     periods a pass stores a complete aligned 16 bytes); periods with window edges or unaligned rows are flagged
+//     warp-wide and take a general byte-store path.
 #ifndef MUA_DL_WARPS
 #define MUA_DL_WARPS 14        // 8: 1.67 ms, 10: 1.45, 12: 1.32, 14: 1.20, 16: 1.22, 18: 1.27 (96 registers, spills), 20: 1.35
 #endif
 constexpr int DL_WARPS = MUA_DL_WARPS;           // launched warps (more do not help: see profiles/r01_summary.md); those with a buffer in the runtime layout work
 constexpr int DL_ROW_B = 144;          // stream ring row: 128 B + 16 B pad
-#ifndef MUA_DL_BRANCHFREE
-#define MUA_DL_BRANCHFREE 1
-#endif
-#ifndef MUA_DL_FASTWO
-#define MUA_DL_FASTWO 1
-#endif
 constexpr int DL_OUT_B = 144;          // output tile row: 128 B + 16 B pad (row starts 4 banks apart)
 constexpr int DL_MAX_ROWS = 3;         // codebook rows (K) whose lane-replicated tables fit
 constexpr int DL_TAB_B = 256 * 32 * 4; // one lane-replicated table: 32 KB
@@ -544,7 +540,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                     slow |= (1u << ((R + 127) >> 7)) - 1u;                            // unaligned row: byte stores throughout
                 }
             }
-            wslow[c] = MUA_DL_FASTWO ? __reduce_or_sync(FULL, slow) : 0xFFFFFFFFu;
+            wslow[c] = __reduce_or_sync(FULL, slow);
             // position of the chunk's first bit in the ring frame
             const uint32_t boff =
                 (uint32_t)(reinterpret_cast<unsigned long long>(cur[c].sbase) + (cur[c].bp >> 3) - R[c].org) * 8 + (cur[c].bp & 7);
@@ -576,7 +572,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     w0[c] = stream_rev(rowp[c][rp[c]]); w1[c] = stream_rev(rowp[c][rp[c] + 1]);
-                    wn[c] = MUA_DL_BRANCHFREE ? rowp[c][rp[c] + 2] : stream_rev(rowp[c][rp[c] + 2]);
+                    wn[c] = rowp[c][rp[c] + 2];                                          // kept raw, see the refill below
                     rp[c] += 3;
                 }
             }
@@ -605,7 +601,6 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     off[c] += o[c];
-#if MUA_DL_BRANCHFREE
                     {   // branch-free refill: the word after next is read every time and kept RAW (it is bit-reversed when it
                         // moves into w1, a refill later, so nothing ever waits for this load)
                         const bool rf = off[c] >= 32;
@@ -617,9 +612,6 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                         rp[c] += rf ? 1u : 0u;
                         off[c] -= rf ? 32u : 0u;
                     }
-#else
-                    if (off[c] >= 32) { w0[c] = w1[c]; w1[c] = wn[c]; wn[c] = stream_rev(rowp[c][rp[c] & 31]); ++rp[c]; off[c] -= 32; }
-#endif
                     reinterpret_cast<uint4*>(s_out[c] + lane * DL_OUT_B)[q] = make_uint4(ow[c][0], ow[c][1], ow[c][2], ow[c][3]);
                 }
             }
@@ -883,6 +875,37 @@ __global__ void __launch_bounds__(256) k_bin_sym_wide(const uint8_t* __restrict_
             reinterpret_cast<uint4*>(dst)[q] = make_uint4(o[0], o[1], o[2], o[3]);
         } else {
             for (int k = 0; k < 16 && b0 + 16 * q + k < nb; ++k) dst[16 * q + k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+        }
+    }
+}
+
+// Events -> saturated bin counts, one thread per event (grid stride).  The bin is found by division and then
+// corrected against the float64 edges t0 + k*w (separately rounded multiply and add, as NumPy / MATLAB compute
+// them), so the result equals a histogram over those edges bit for bit.  Counts live in the output bytes themselves:
+// a saturating byte increment by compare-and-swap on the containing word (a byte never exceeds `sat`, so nothing
+// carries into its neighbours) -- no workspace, and at MUA rates (a few events per bin) hardly any contention.
+__global__ void __launch_bounds__(256) k_bin_events(const double* __restrict__ times, const int32_t* __restrict__ chan, int64_t N,
+                                                    double t0, double w, int64_t nb, int C, uint8_t* __restrict__ sym,
+                                                    int64_t stride, uint32_t sat) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = times[i];
+        const int c = chan[i];
+        if (c < 0 || c >= C || !(x >= t0)) continue;                     // also drops NaN
+        auto edge = [&](int64_t k) { return __dadd_rn(t0, __dmul_rn((double)k, w)); };
+        if (x > edge(nb)) continue;
+        double q = floor((x - t0) / w);
+        int64_t k = q < 0.0 ? 0 : (q > (double)nb ? nb : (int64_t)q);
+        while (k > 0 && x < edge(k)) --k;
+        while (k < nb && x >= edge(k + 1)) ++k;
+        if (k == nb) k = nb - 1;                                         // x == last edge: the last bin is closed
+        uint8_t* bp = sym + (int64_t)c * stride + k;
+        uint32_t* wp = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(bp) & ~(uintptr_t)3);
+        const int sh = 8 * (int)(reinterpret_cast<uintptr_t>(bp) & 3);
+        uint32_t old = *wp;
+        while (((old >> sh) & 0xFFu) < sat) {
+            const uint32_t seen = atomicCAS(wp, old, old + (1u << sh));
+            if (seen == old) break;
+            old = seen;
         }
     }
 }

@@ -40,3 +40,21 @@ def recording_from_mat(path, key="binned_MUA", device="cuda", bin_res=1, S=None)
     assert m.ndim == 2, "binned_MUA must be [n_bins, n_channels]"
     raster = torch.from_numpy(np.ascontiguousarray(m, dtype=np.uint8)).to(device)
     return P.bin_raster(raster, int(bin_res), S=S, counts=False)
+
+
+def recording_from_spike_times(spike_times, BP_ms, t_start=None, t_end=None, device="cuda", S=None):
+    """Per-channel lists of threshold-crossing times (s) -> channel-major Recording of bin counts, the MATLAB formatters'
+    `histogram2(times, channel, min(t):BP/1000:max(t), ...)` + `uint8(...)` (Data/Load_and_bin_Sabes_store_as_mat_file.m:
+    41-54): times are offset by `t_start` (default: the first event), the edges run from 0 in steps of BP/1000 up to
+    `t_end - t_start` (default: the last event), `floor(span / w)` whole bins.  Binning runs on the GPU (mua_bin_events)."""
+    lens = [len(x) for x in spike_times]
+    times = np.concatenate([np.asarray(x, dtype=np.float64) for x in spike_times]) if sum(lens) else np.zeros(0)
+    chan = np.repeat(np.arange(len(spike_times), dtype=np.int32), lens)
+    first = float(times.min()) if t_start is None else float(t_start)
+    last = float(times.max()) if t_end is None else float(t_end)
+    w = BP_ms / 1000
+    span = last - first
+    nb = int(np.floor(span / w + 1e-9)) if span > 0 else 0
+    t = torch.from_numpy(times - first).to(device)
+    c = torch.from_numpy(chan).to(device)
+    return P.bin_events(t, c, 0.0, w, nb, len(spike_times), S=S)

@@ -329,6 +329,23 @@ def bin_raster(raster: torch.Tensor, bin_res: int, S: Optional[int] = None, coun
         return Recording(sym=sym, C=int(Cn), T=int(nb), stride=int(stride))
 
 
+def bin_events(times: torch.Tensor, chan: torch.Tensor, t0: float, w: float, nb: int, n_channels: int, S: Optional[int] = None):
+    """MUA events -> binned count symbols (mua_bin_events; the MATLAB formatters' histogram2,
+    Data/Load_and_bin_Sabes_store_as_mat_file.m:49-54).  times float64 [N] (s), chan int32 [N] on the device;
+    bin k = [t0 + k*w, t0 + (k+1)*w), last bin closed.  Returns a Recording of uint8 counts saturated at S-1
+    (S None: at 255, MATLAB's uint8 cast)."""
+    lib = _lib.load()
+    times = times.contiguous()
+    chan = chan.contiguous()
+    assert times.dtype == torch.float64 and chan.dtype == torch.int32 and times.numel() == chan.numel()
+    stride = max(_round16(nb), 16)
+    sym = torch.empty((int(n_channels), stride), dtype=torch.uint8, device=times.device)
+    with torch.cuda.device(times.device):
+        _lib.check(lib.mua_bin_events(_ptr(times), _ptr(chan), times.numel(), float(t0), float(w), int(nb), int(n_channels),
+                                      _ptr(sym), stride, int(S or 0), _stream()))
+    return Recording(sym=sym, C=int(n_channels), T=int(nb), stride=int(stride))
+
+
 def synth_threshold_table(BP_ms: float) -> np.ndarray:
     """uint32 [256][24] Poisson-CDF thresholds per rate class (rates = Gamma(2,10) Hz quantiles x BP);
     configuration data for the synthetic generator, same formula as oracle/mua_oracle.py."""

@@ -88,6 +88,18 @@ int mua_build_tables(void* d_tables, const uint8_t* h_lens, const uint16_t* h_co
 int mua_bin_raster(const void* d_raster, int dtype, int64_t T0, int32_t C, int32_t bin_res,
                    int64_t* d_counts, uint8_t* d_sym, int64_t sym_stride, int32_t S, void* stream);
 
+/* MUA events (threshold-crossing times) -> binned count symbols: the MATLAB formatters' histogram2 over
+ * `time_bins = min(t):BP/1000:max(t)` and one bin per channel, cast to uint8
+ * (Data/Load_and_bin_Sabes_store_as_mat_file.m:49-54; same in the Flint and Brochier formatters).
+ *   d_times : float64 [N] event times in seconds, any order;  d_chan : int32 [N] channel of every event (0-based)
+ *   edge k  = t0 + k*w, computed in float64 as add(t0, mul(k, w)); bin k = [edge k, edge k+1), the last bin is
+ *             closed on the right (histogram / np.histogram convention); events outside [edge 0, edge nb],
+ *             events of channels outside [0, C) and NaN times are dropped
+ *   d_sym   : uint8 [C][sym_stride] channel-major counts saturated at S-1 (S = 0: at 255, the uint8 cast);
+ *             the call zeroes d_sym first (sym_stride >= nb, multiple of 4, d_sym 4-byte aligned) */
+int mua_bin_events(const double* d_times, const int32_t* d_chan, int64_t N, double t0, double w, int64_t nb,
+                   int32_t C, uint8_t* d_sym, int64_t sym_stride, int32_t S, void* stream);
+
 /* ---- stages 2-4: calibration windows, histograms, approx-sort, SCLV selection ------------- */
 
 /* For every channel c and history length H_h (h < nH):

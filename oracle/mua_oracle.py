@@ -59,6 +59,23 @@ def bin_mua_data(MUA: np.ndarray, bin_res: int) -> np.ndarray:
 # --------------------------------------------------------------------------------------------
 # a2/a3  saturation and calibration length          functions_1.py:27-68, get_BR_no_sort.py:164
 # --------------------------------------------------------------------------------------------
+def bin_events(times: np.ndarray, chan: np.ndarray, t0: float, w: float, nb: int, C: int, sat: int = 255) -> np.ndarray:
+    """MUA events -> [C, nb] bin counts saturated at `sat`: histogram2 over `time_bins = t0 : w : ...` and one bin per
+    channel, cast to uint8 (Data/Load_and_bin_Sabes_store_as_mat_file.m:49-54).  Edges t0 + k*w in float64; bins
+    half-open, the last one closed (np.histogram's convention, which is histogram2's); events outside the edges are
+    dropped.  MATLAB is not runnable here: this function (NumPy's histogram over the same edges) is the definition."""
+    edges = t0 + np.arange(nb + 1, dtype=np.float64) * w
+    out = np.zeros((C, nb), dtype=np.int64)
+    times = np.asarray(times, dtype=np.float64)
+    chan = np.asarray(chan)
+    for c in range(C):
+        x = times[chan == c]
+        x = x[~np.isnan(x)]
+        if nb:
+            out[c] = np.histogram(x, bins=edges)[0]
+    return np.minimum(out, sat).astype(np.uint8)
+
+
 def saturate(x: np.ndarray, S: int) -> np.ndarray:
     """x[x > S-1] = S-1 (get_BR_no_sort.py:143,164; test_chosen_system.py:83); returns a copy."""
     return np.minimum(x, S - 1).astype(x.dtype)

@@ -307,3 +307,35 @@ def test_degenerate_recordings():
     es0 = P.encode(empty, cb, z, z, z.to(torch.uint8), z.to(torch.uint8))
     assert es0.total_bits.numel() == 0 and int(es0.overflow.item()) == 0
     assert P.train_hist(empty, S).shape == (0, S)
+
+
+def test_bin_events_matches_histogram():
+    """Threshold-crossing times -> binned count symbols (mua_bin_events; the MATLAB formatters' histogram2 + uint8 cast)
+    against NumPy's histogram over the same float64 edges: events exactly on edges, on the closed last edge, outside the
+    range, NaN times, channels out of range, a bin with more than 255 events, both saturation modes, no events, no bins."""
+    rng = np.random.default_rng(8)
+    for (C, nb, t0, w, N) in [(50, 1000, 0.3, 0.05, 200000), (7, 333, -2.0, 0.001, 30000), (3, 1, 0.0, 0.1, 500), (5, 100, 10.0, 0.02, 0)]:
+        edges = t0 + np.arange(nb + 1, dtype=np.float64) * w
+        times = rng.uniform(t0 - 3 * w, edges[-1] + 3 * w, size=N)
+        chan = rng.integers(-1, C + 1, size=N).astype(np.int32)
+        if N:
+            k = rng.integers(0, nb + 1, size=min(N, 400))
+            times[:len(k)] = edges[k]                                   # exactly on edges (incl. the last, closed one)
+            times[len(k):len(k) + 300] = edges[nb // 2] + 0.25 * w      # a hot bin: > 255 events in one channel
+            chan[len(k):len(k) + 300] = 1
+            times[len(k) + 300:len(k) + 310] = np.nan
+        dt, dc = torch.from_numpy(times).to(DEV), torch.from_numpy(chan).to(DEV)
+        for S in (None, 3, 10):
+            rec = P.bin_events(dt, dc, t0, w, nb, C, S=S)
+            want = O.bin_events(times, chan, t0, w, nb, C, sat=255 if S is None else S - 1)
+            assert rec.T == nb and rec.C == C
+            got = rec.sym.cpu().numpy()
+            assert np.array_equal(got[:, :nb], want) and not got[:, nb:].any()
+    # no bins / the list-of-channels front end
+    assert P.bin_events(torch.zeros(3, dtype=torch.float64, device=DEV), torch.zeros(3, dtype=torch.int32, device=DEV), 0.0, 0.1, 0, 4).T == 0
+    spikes = [np.sort(rng.uniform(5.0, 65.0, size=int(n))) for n in (1200, 0, 3000, 40)]
+    rec = mio.recording_from_spike_times(spikes, BP_ms=50, S=3)
+    first, last = min(s.min() for s in spikes if len(s)), max(s.max() for s in spikes if len(s))
+    nb = int(np.floor((last - first) / 0.05 + 1e-9))
+    want = O.bin_events(np.concatenate(spikes) - first, np.repeat(np.arange(4), [len(s) for s in spikes]), 0.0, 0.05, nb, 4, sat=2)
+    assert rec.T == nb and np.array_equal(rec.sym.cpu().numpy()[:, :nb], want)
