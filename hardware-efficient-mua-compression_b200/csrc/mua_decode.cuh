@@ -642,7 +642,13 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                         uint8_t* d = reinterpret_cast<uint8_t*>(wptr[c][i]) + done;
                         if (vr >= 16 && (wptr[c][i] & 15) == 0) {
                             *reinterpret_cast<uint4*>(d) = v[i];
-                        } else if (vr > 0) {   // window edge or unaligned first chunk: byte stores
+                        } else if (vr >= 16 && (wptr[c][i] & 7) == 0) {   // first chunk of a window that starts on an 8-byte boundary
+                            reinterpret_cast<uint2*>(d)[0] = make_uint2(v[i].x, v[i].y);
+                            reinterpret_cast<uint2*>(d)[1] = make_uint2(v[i].z, v[i].w);
+                        } else if (vr >= 16 && (wptr[c][i] & 3) == 0) {   // ... on a 4-byte boundary
+                            reinterpret_cast<uint32_t*>(d)[0] = v[i].x; reinterpret_cast<uint32_t*>(d)[1] = v[i].y;
+                            reinterpret_cast<uint32_t*>(d)[2] = v[i].z; reinterpret_cast<uint32_t*>(d)[3] = v[i].w;
+                        } else if (vr > 0) {   // window edge or odd start: byte stores
                             const uint8_t* sp = s_out[c] + r * DL_OUT_B + wcol * 16;
                             const int nbyte = min(16, vr);
                             for (int k = 0; k < nbyte; ++k) d[k] = sp[k];

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import mua_b200
 from mua_b200 import pipeline as P
-C, T, H = 125000, 72000, 64
+C, T = 125000, 72000
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 cb = mua_b200.Codebook(3, np.array([[1, 2, 2]]), device="cuda")
 rec = P.synth_recording(C, T, seed=1, BP_ms=50.0, bursty=True, device="cuda")
 cal = P.calibrate(rec, cb, [H], use_sort=True, window="truncate")
@@ -22,4 +23,4 @@ def timeit(fn, n=10):
 t_enc = timeit(lambda: P.encode(rec, cb, st, en, pk, ec, out=es))
 t_dec = timeit(lambda: P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=H + T // 2))
 bad = int(P.verify(rec, dec, 3, st, en).item())
-print(json.dumps({"lib": sys.argv[1] if len(sys.argv) > 1 else "", "encode_ms": round(t_enc, 4), "decode_ms": round(t_dec, 4), "mismatch": bad}))
+print(json.dumps({"lib": sys.argv[1] if len(sys.argv) > 1 else "", "H": H, "encode_ms": round(t_enc, 4), "decode_ms": round(t_dec, 4), "mismatch": bad}))
