@@ -284,3 +284,34 @@ def test_full_size_roundtrip_properties():
         want, total, offs = O.encode_channel(xs[i], int(stc[c]), int(enc_[c]), S, rank, cb.codes[0], cb.lens[0])
         assert tb[c] == total and np.array_equal(es.channel_bytes(int(c)), want)
         assert np.array_equal(_cpu(es.chunk_off[int(c)]).view(np.uint32)[:len(offs)], offs)
+
+
+def test_cfg5_shard_spot_parity():
+    """The bench workload itself (one GPU's shard of cfg5: 125 000 channels x 72 000 bins, chosen system): bit counts of
+    EVERY channel equal SCLV . post histogram, decode lossless, and the streams / chunk offsets of spot channels
+    (first, last, random) equal the oracle's on channels regenerated from the counter RNG -- with a channel offset as
+    rank 3 of an 8-GPU run would have."""
+    C, T, S, H, c0 = 125000, 72000, 3, 64, 3 * 125000
+    thr = O.synth_threshold_table(50.0)
+    rec = P.synth_recording(C, T, seed=6, BP_ms=50.0, bursty=True, c0=c0, device=DEV, thr=thr)
+    cb = mua_b200.Codebook(S, np.array([[1, 2, 2]]), device=DEV)
+    cal = P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=("cutoff", "end", "peak", "enc"))       # head kernel
+    st, en, pk, ec = (cal[k][:, 0] for k in ("cutoff", "end", "peak", "enc"))
+    es = P.encode(rec, cb, st, en, pk, ec, slot_bytes=cb.worst_case_slot_bytes(T // 2 + 16))
+    dec = P.decode(es, rec, cb, st, en, pk, ec, max_end=H + T // 2)
+    assert int(es.overflow.item()) == 0 and int(P.verify(rec, dec, S, st, en).item()) == 0
+    full = P.calibrate(rec, cb, [H], use_sort=True, window="truncate")                                           # general kernel
+    for k in ("cutoff", "end", "peak", "enc"):
+        assert torch.equal(full[k], cal[k]), k
+    assert torch.equal(es.total_bits, full["bits"][:, 0])
+    pick = np.unique(np.concatenate([[0, 1, C - 1], np.random.default_rng(1).choice(C, size=13, replace=False)]))
+    xs = O.synth_symbols(6, c0 + pick, T, thr, True)
+    for i, c in enumerate(pick):
+        c = int(c)
+        assert np.array_equal(rec.channel_to_host(c), xs[i])
+        cutoff, end, a, p, _ = O.window_hists(xs[i], S, H, skip_rule=False)
+        assert (int(st[c]), int(en[c]), int(pk[c])) == (cutoff, end, int(np.argmax(a)))
+        want, total, offs = O.encode_channel(xs[i], cutoff, end, S, O.rank_of_symbol(int(np.argmax(a)), S), cb.codes[0], cb.lens[0])
+        assert int(es.total_bits[c]) == total and np.array_equal(es.channel_bytes(c), want)
+        assert np.array_equal(_cpu(es.chunk_off[c]).view(np.uint32)[:len(offs)], offs)
+        assert np.array_equal(rec.channel_to_host(c, dec)[cutoff:end], np.minimum(xs[i][cutoff:end], S - 1))
