@@ -78,7 +78,10 @@ void layout_sizes(int S, int K, int Lmax, TabHdr* h) {
         next = align_up(next + S * K * 512, 512);
     }
     h->dec_off = next;
-    h->total_bytes = align_up(h->dec_off + ((S * K) << h->W) * 4, 512);
+    next = align_up(h->dec_off + ((S * K) << h->W) * 4, 512);
+    h->Wv = decv_window(K, Lmax);
+    h->decv_off = next;
+    h->total_bytes = align_up(h->decv_off + (K << h->Wv) * 4, 512);
 }
 
 template <int SS, bool MULTI>
@@ -490,6 +493,12 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
 #ifndef MUA_DL_NC
 #define MUA_DL_NC 1
 #endif
+#ifndef MUA_DECODE_VAR
+#define MUA_DECODE_VAR 1
+#endif
+#ifndef MUA_DV_PPS
+#define MUA_DV_PPS 1          // 128-symbol periods per staged stream row of k_decode_var
+#endif
             constexpr int NC = MUA_DL_NC;
             cudaError_t e = cudaFuncSetAttribute(k_decode_lane<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
@@ -513,6 +522,27 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
             cudaError_t e = cudaFuncSetAttribute(k_decode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
             k_decode_fast<false><<<grid, DF_WARPS * 32, smem, st>>>(P);
+        }
+    } else if (MUA_DECODE_VAR && h.decv_off) {
+        // variable-count lookups from per-row rank tables in shared memory: one persistent CTA per SM
+        const int fixed = 4 * MUA_MAX_S * 4 + (h.K << h.Wv) * 4;
+        P.var_pps = MUA_DV_PPS;
+        P.var_str_w = ((127 + 64 + P.var_pps * 131 * h.Lmax + 31) / 32 + 3) / 4 * 4;     // whole 16-byte units
+        const int DV_PER_WARP = 32 * P.var_str_w * 4 + 32 * DG_OUT_B + 16;
+        int nw = (227 * 1024 - fixed) / DV_PER_WARP;
+        nw = nw > DV_WARPS ? DV_WARPS : nw;
+        REQUIRE(nw >= 1, "decode tables do not fit shared memory");
+        const int smem = nw * DV_PER_WARP + fixed;
+        const long long blocks_needed = (groups + nw - 1) / nw;
+        const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
+        if (h.S > 8) {
+            cudaError_t e = cudaFuncSetAttribute(k_decode_var<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+            k_decode_var<true><<<grid, nw * 32, smem, st>>>(P);
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(k_decode_var<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+            k_decode_var<false><<<grid, nw * 32, smem, st>>>(P);
         }
     } else {
         const int smem = DG_WARPS * DG_PER_WARP + (smem_lut ? lut_bytes : 0);

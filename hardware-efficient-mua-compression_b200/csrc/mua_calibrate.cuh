@@ -77,6 +77,26 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
         }
         dec[v] = e | ((uint32_t)used << 28);
     }
+    if (p == 0) {   // variable-count rank table of row k (the rank -> symbol map of the lane's peak is applied at decode time)
+        const int Wv = T->Wv;
+        uint32_t* decv = reinterpret_cast<uint32_t*>(blob + T->decv_off) + ((size_t)k << Wv);
+        const uint32_t none = S <= 8 ? 0x8u : 0xFu;
+        for (int v = tid; v < (1 << Wv); v += blockDim.x) {
+            uint32_t sel = none * 0x1111u;
+            int used = 0, n = 0;
+            for (; n < 4; ++n) {
+                int hit = -1;
+                for (int r = 0; r < S; ++r) {
+                    const int l = s_len[r];
+                    if (used + l <= Wv && (uint32_t)((v >> (Wv - used - l)) & ((1 << l) - 1)) == s_code[r]) { hit = r; break; }
+                }
+                if (hit < 0) break;   // the next codeword does not fit the window any more
+                sel = (sel & ~(0xFu << (4 * n))) | ((uint32_t)hit << (4 * n));
+                used += s_len[hit];
+            }
+            decv[v] = sel | ((uint32_t)n << 16) | ((uint32_t)used << 20);
+        }
+    }
 }
 
 // sum of the four byte counters of a packed word (each <= 252)

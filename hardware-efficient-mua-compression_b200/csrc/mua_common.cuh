@@ -21,12 +21,17 @@ constexpr int TILE = MUA_CHUNK;        // symbols per warp tile == decode chunk
 //                             256 + 2i; only when Lmax <= 8 (pair encoder)
 // dec  : uint32 [S][K][1<<W]  W = nsym*Lmax bit window -> nsym symbols, one per byte (first symbol in
 //                             byte 0, values < 16) | used_bits << 28
+// decv : uint32 [K][1<<Wv]     Wv-bit window -> as many whole symbols as fit, at most 4, as RANKS of codebook row k:
+//                             bits [15:0] four PRMT byte selectors into the lane's rank -> symbol map (unused slots
+//                             select a zero byte: 0x8 = sign replicate for S <= 8, 0xF = entry 15 of the 16-byte
+//                             map for S >= 9), [18:16] symbol count (>= 1: Wv >= Lmax), [23:20] bits used
 struct TabHdr {
     int32_t S, K, Lmax, W;
     int32_t nsym;                    // symbols decoded per LUT lookup (4, 2 or 1)
     int32_t enc1_off, enc2_off, enc4_off, dec_off, total_bytes;
     int32_t encp_off;                // 0 when Lmax > 8
-    int32_t pad[5];
+    int32_t decv_off, Wv;            // variable-count rank tables of the general decoder: uint32 [K][1 << Wv]
+    int32_t pad[3];
     uint8_t lens[MUA_MAX_K][16];     // SCLV rows (Stored_SCLVs_S_<S>.pkl), ascending lengths
     uint16_t codes[MUA_MAX_K][16];   // codeword of rank r
     uint8_t rank[MUA_MAX_S][16];     // rank[p][s]: approx_sort permutation for peak p (functions_1.py:75-90)
@@ -59,6 +64,13 @@ __host__ __device__ inline int rank_of(int p, int s, int S) {
     if (s < p) return 2 * (p - s) - 1;
     if (s <= 2 * p) return 2 * (s - p);
     return s;
+}
+
+// window of the variable-count decode tables: as wide as keeps K tables within 64 KB (72 KB for S = 10), 9..12 bits
+__host__ __device__ inline int decv_window(int K, int Lmax) {
+    int W = 12;
+    while (W > 9 && (long long)K * (1ll << W) * 4 > 64 * 1024) --W;
+    return W < Lmax ? Lmax : W;
 }
 
 struct Layout {

@@ -21,6 +21,7 @@ struct DecParams {
     const uint8_t* tab;
     int32_t K, Lmax;
     uint8_t* dec;
+    int32_t var_str_w, var_pps;   // k_decode_var: staged stream words per lane and stage, 128-symbol periods per stage
 };
 
 // ---- general decoder (any codebook) ----
@@ -165,6 +166,166 @@ __global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_co
                         } else {   // window edge or unaligned first chunk: byte stores
                             const int nbyte = min(16, vr - col * 16);
                             for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
+                        }
+                    }
+                }
+                __syncwarp();
+                if (rem > 0) { rem -= 128; done += 128; }
+            }
+            bitpos += consumed;
+            if (rem <= 0) rem = 0;
+        }
+    }
+}
+
+// ---- general decoder with variable-count lookups (every codebook the lane / fast decoders do not take) ----
+// k_decode_gen decodes a FIXED number of symbols per lookup (1 for S >= 7: W = Lmax bits) from per-(peak,row) tables
+// that outgrow shared memory (S = 9: 212 KB, read through L1/L2): 17 instructions and one global load per symbol.
+// Here a lookup decodes AS MANY whole symbols as its Wv-bit window holds (at most 4; the SCLV codes of skewed MUA
+// counts are 1..2 bits for the frequent symbols, so mostly 4) from rank tables per codebook ROW (K x 2^Wv entries,
+// <= 72 KB: always in shared memory); the lane's peak is applied by the PRMT that unpacks an entry (S <= 8: one PRMT
+// into the 8-byte rank -> symbol map; S >= 9: two PRMTs into the halves of the 16-byte map and a select).  Decoded
+// symbols are appended to a 64-bit register queue and leave for the output tile one 4-byte word at a time, so the
+// tile and the write-out are those of the fixed-count decoders.  Same chunk bookkeeping and stream staging (one TMA
+// bulk copy per lane and stage, sized for MUA_DV_PPS periods) as k_decode_gen.  One persistent CTA per SM with as many warps as fit beside
+// the tables.
+constexpr int DV_WARPS = 20;            // at most; the launch takes as many as fit beside the tables
+
+template <bool WIDE>
+__global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_constant__ DecParams P) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
+    const int K = T->K, Wv = T->Wv;
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->decv_off == 0 || (WIDE != (T->S > 8))) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int STR_W = P.var_str_w;                                                   // staged stream words per lane
+    const int per_warp = 32 * STR_W * 4 + 32 * DG_OUT_B + 16;
+    uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * per_warp);
+    uint8_t* s_out = dsm + warp * per_warp + 32 * STR_W * 4;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + 32 * DG_OUT_B);
+    uint32_t* s_map = reinterpret_cast<uint32_t*>(dsm + nwarps * per_warp);          // uint4 [MUA_MAX_S]: idx[p][0..15]
+    uint32_t* s_tab = s_map + 4 * MUA_MAX_S;
+    if (lane == 0) {
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
+    {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(P.tab + T->decv_off);
+        for (int i = threadIdx.x; i < (K << Wv); i += blockDim.x) s_tab[i] = g[i];
+        const uint32_t* gi = reinterpret_cast<const uint32_t*>(&T->idx[0][0]);
+        for (int i = threadIdx.x; i < 4 * MUA_MAX_S; i += blockDim.x) s_map[i] = gi[i];
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    // a period decodes 128 symbols and may run up to 3 symbols ahead (they wait in the register queue); the host sized
+    // the staged row for var_pps periods: 127 bits of alignment slack + var_pps * 131 * Lmax + 64 bits of look-ahead
+    const int periods_per_stage = P.var_pps;
+    const long long nitems = (long long)P.C * P.item_chunks;
+    const long long ngroups = (nitems + 31) / 32;
+    const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
+    const uint32_t wshift = 32 - Wv;
+
+    for (long long g = (long long)blockIdx.x * nwarps + warp; g < ngroups; g += (long long)gridDim.x * nwarps) {
+        const long long item = g * 32 + lane;
+        int rem = 0;
+        uint32_t bitpos = 0;
+        const uint8_t* sbase = P.stream;
+        uint8_t* optr = P.dec;
+        const uint32_t* tab = s_tab;
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (item < nitems) {
+            const int c = (int)(item / P.item_chunks), j = (int)(item % P.item_chunks);
+            const int start = P.start[c], end = P.end[c];
+            if (end > start && start >= 0) {
+                const int j0 = start / TILE;
+                const int nch = (end + TILE - 1) / TILE - j0;
+                if (j < nch) {
+                    const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
+                    rem = b - a;
+                    bitpos = P.chunk_off[(size_t)c * P.chunk_stride + j];
+                    sbase = P.stream + (size_t)c * P.slot_bytes;
+                    optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
+                    tab += (size_t)P.enc[c] << Wv;
+                    const uint4 mp = reinterpret_cast<const uint4*>(s_map)[P.peak[c]];
+                    m0 = mp.x; m1 = mp.y; m2 = mp.z; m3 = mp.w;
+                }
+            }
+        }
+        int done = 0;                                            // symbols already written out
+        unsigned long long queue = 0;                            // decoded symbols not yet in the tile, one per byte
+        uint32_t fill8 = 0;                                      // 8 x their number (0, 8, 16, 24)
+        while (__any_sync(FULL, rem > 0)) {
+            // ---- stage 272 stream bytes per lane (one TMA bulk copy each), from the 16-byte unit holding `bitpos` ----
+            const uint32_t cur_al = (bitpos >> 7) << 4;
+            const uint32_t nbytes = rem > 0 ? min((uint32_t)(STR_W * 4), slot_bytes - cur_al) : 0u;
+            const uint32_t total = __reduce_add_sync(FULL, nbytes);
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (total) {
+                if (lane == 0) mbar_expect_tx(s_bar, total);
+                __syncwarp();
+                if (nbytes) tma_load_1d(s_str + lane * STR_W, sbase + cur_al, nbytes, s_bar);
+                mbar_wait(s_bar, parity);
+                parity ^= 1;
+            }
+            const uint32_t* rowp = s_str + lane * STR_W;
+            const uint32_t boff = bitpos - cur_al * 8;           // 0..127
+            uint32_t rp = boff >> 5;
+            uint32_t hi = bswap32(rowp[rp]), lo = bswap32(rowp[rp + 1]);
+            rp += 2;
+            uint32_t off = boff & 31;
+            uint32_t consumed = 0;                               // bits consumed in this stage
+
+            for (int per = 0; per < periods_per_stage && __any_sync(FULL, rem > 0); ++per) {
+                // ---- 128 symbols per lane into the output tile ----
+                uint32_t* orow = reinterpret_cast<uint32_t*>(s_out + lane * DG_OUT_B);
+                uint32_t wpos = 0;                               // words of this period's tile row already written
+                while (__any_sync(FULL, wpos < 32)) {
+                    const bool act = wpos < 32;
+                    const uint32_t x = __funnelshift_l(lo, hi, off);
+                    const uint32_t e = tab[x >> wshift];
+                    uint32_t syms;
+                    if (!WIDE) {
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(syms) : "r"(m0), "r"(m1), "r"(e));
+                    } else {
+                        uint32_t slo, shi, msk;
+                        const uint32_t e7 = e & 0x7777u;
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(slo) : "r"(m0), "r"(m1), "r"(e7));
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(shi) : "r"(m2), "r"(m3), "r"(e7));
+                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(msk) : "r"(0x0000FF00u), "r"(0u), "r"((e >> 3) & 0x1111u));
+                        syms = (slo & ~msk) | (shi & msk);
+                    }
+                    syms = act ? syms : 0u;
+                    const uint32_t cnt8 = act ? (e >> 13) & 0x38u : 0u;
+                    const uint32_t used = act ? (e >> 20) & 0xFu : 0u;
+                    queue |= (unsigned long long)syms << fill8;
+                    fill8 += cnt8;
+                    if (fill8 >= 32) {
+                        orow[wpos] = (uint32_t)queue;
+                        ++wpos;
+                        queue >>= 32;
+                        fill8 -= 32;
+                    }
+                    off += used;
+                    consumed += used;
+                    if (off >= 32) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(STR_W - 1))]); ++rp; off -= 32; }
+                }
+                __syncwarp();
+                // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
+                const int vrow_self = min(max(rem, 0), 128);     // valid bytes of my row in this period
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3), col = lane & 7;
+                    const int vr = __shfl_sync(FULL, vrow_self, r);
+                    const unsigned long long dptr = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(optr) + done, r);
+                    if (col * 16 < vr) {
+                        const uint8_t* sp = s_out + r * DG_OUT_B + col * 16;
+                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
+                        if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
+                            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
+                        } else {   // window edge or unaligned first chunk: byte stores
+                            const int nbyte = min(16, vr - col * 16);
+                            for (int kk = 0; kk < nbyte; ++kk) d[kk] = sp[kk];
                         }
                     }
                 }
