@@ -3,7 +3,7 @@
 (canonical or the generator's codewords), SCLV row subset, history lengths, window rule, sort mode and ragged
 recordings; every calibrate output, every stream byte, every chunk offset and the decoded symbols are compared.
 
-  python tools/fuzz_parity.py [seconds=120] [seed=0]        prints one JSON line; exit code 1 on the first mismatch"""
+  python tests/fuzz_parity.py [seconds=120] [seed=0]        prints one JSON line; exit code 1 on the first mismatch"""
 import json
 import os
 import sys

@@ -54,13 +54,14 @@ def test_shipped_tables_equal_oracle_tables():
 
 
 def test_no_product_import_of_oracle():
-    """The product package must never import anything under oracle/."""
-    pkg = os.path.join(ROOT, "hardware-efficient-mua-compression_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+    """The product package (and the helper scripts under tools/) must never import anything under oracle/: the oracle is
+    test infrastructure, reachable only from tests/, smoke() and bench.py's CPU-baseline legs."""
+    for top in ("hardware-efficient-mua-compression_b200", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
 
 
 _WORKER = r'''

@@ -1,4 +1,4 @@
-"""Randomised differential test against the oracle (tools/fuzz_parity.py): random alphabet size, codebook, SCLV row subset,
+"""Randomised differential test against the oracle (tests/fuzz_parity.py): random alphabet size, codebook, SCLV row subset,
 history lengths, window rule, sort mode and ragged recordings; 400 configurations here, 31 000 in the round's GPU run
 (profiles/r01_summary.md)."""
 import importlib.util
@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_random_configurations_match_oracle():
-    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT, "tools", "fuzz_parity.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT, "tests", "fuzz_parity.py"))
     fz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fz)
     rng = np.random.default_rng(2024)
