@@ -496,6 +496,9 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 //   * the write-out (8 lanes per 128-byte row) uses per-group precomputed row pointers and store counts (for how many
 //     periods a pass stores a complete aligned 16 bytes); periods with window edges or unaligned rows are flagged
 //     warp-wide and take a general byte-store path.
+#ifndef MUA_DL_TICKETS
+#define MUA_DL_TICKETS 1
+#endif
 #ifndef MUA_DL_WARPS
 #define MUA_DL_WARPS 14        // 8: 1.67 ms, 10: 1.45, 12: 1.32, 14: 1.20, 16: 1.22, 18: 1.27 (96 registers, spills), 20: 1.35
 #endif
@@ -624,6 +627,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                 for (int r = 0; r < 4; ++r) m |= (uint32_t)T->idx[p][4 * h + r] << (8 * r);
             reinterpret_cast<uint32_t*>(dsm)[threadIdx.x] = m;
         }
+        if (threadIdx.x == 16) reinterpret_cast<uint32_t*>(dsm)[16] = (uint32_t)nw;     // next group ticket of this CTA
     }
     __syncthreads();
     if (warp >= nw) return;
@@ -658,6 +662,11 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
         }
     };
 
+    // Groups are handed out by ticket: 14 warps are 4 + 4 + 3 + 3 per scheduler, so warps do not run at the same speed;
+    // ticket t of a CTA is the group the static schedule would have given warp t % nw in round t / nw.
+#if MUA_DL_TICKETS
+    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(dsm) + 16;
+#endif
     const long long gstride = (long long)gridDim.x * nw;
     long long g = (long long)blockIdx.x * nw + warp;
     DecItem cur[NC];
@@ -669,8 +678,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     while (g < ngroups) {
-        const long long gn = g + gstride;
-        const long long nlim = gn < ngroups ? nitems : 0;
+        long long gn = g + gstride;
         uint32_t lbase[NC], mlo[NC], mhi[NC], rp[NC], off[NC], w0[NC], w1[NC], wn[NC];
         int rem[NC];
         // write-out roles: in pass i this lane stores 16 bytes of row 4i + wrow of every chain's tile.  Per group and pass
@@ -777,6 +785,13 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                 }
             }
             if (per == nper - 1) {   // every ring of the warp is free: start the next group's chunks before writing this period out
+#if MUA_DL_TICKETS
+                uint32_t tk = 0;
+                if (lane == 0) tk = atomicAdd(s_ticket, 1u);
+                tk = __shfl_sync(FULL, tk, 0);
+                gn = (long long)blockIdx.x * nw + (tk % (uint32_t)nw) + (long long)(tk / (uint32_t)nw) * gstride;
+#endif
+                const long long nlim = gn < ngroups ? nitems : 0;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     cur[c] = dec_finish(P, dec_load(P, (gn * NC + c) * 32 + lane, nlim), K);
