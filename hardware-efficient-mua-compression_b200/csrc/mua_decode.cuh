@@ -204,11 +204,13 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
     uint8_t* s_out = dsm + warp * per_warp + 32 * STR_W * 4;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + 32 * DG_OUT_B);
     uint32_t* s_map = reinterpret_cast<uint32_t*>(dsm + nwarps * per_warp);          // uint4 [MUA_MAX_S]: idx[p][0..15]
-    uint32_t* s_tab = s_map + 4 * MUA_MAX_S;
+    uint32_t* s_ticket = s_map + 4 * MUA_MAX_S;                                      // next group of this CTA (4 words reserved)
+    uint32_t* s_tab = s_ticket + 4;
     if (lane == 0) {
         mbar_init(s_bar, 1);
         fence_barrier_init();
     }
+    if (threadIdx.x == 0) *s_ticket = 0;
     {
         const uint32_t* g = reinterpret_cast<const uint32_t*>(P.tab + T->decv_off);
         for (int i = threadIdx.x; i < (K << Wv); i += blockDim.x) s_tab[i] = g[i];
@@ -225,7 +227,13 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
     const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
     const uint32_t wshift = 32 - Wv;
 
-    for (long long g = (long long)blockIdx.x * nwarps + warp; g < ngroups; g += (long long)gridDim.x * nwarps) {
+    // groups by ticket (the warps of a CTA do not sit evenly on the four schedulers): ticket t = group blockIdx + t * grid
+    for (;;) {
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(s_ticket, 1u);
+        tk = __shfl_sync(FULL, tk, 0);
+        const long long g = (long long)blockIdx.x + (long long)tk * gridDim.x;
+        if (g >= ngroups) break;
         const long long item = g * 32 + lane;
         int rem = 0;
         uint32_t bitpos = 0;
