@@ -204,7 +204,9 @@ def run_b200(a):
     slot = cb.worst_case_slot_bytes(T // 2 + 16)
     es = P.encode(rec, cb, cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0], slot_bytes=slot)
     dec = torch.zeros_like(rec.sym)
-    rep_buf = torch.empty((C_total, 4), dtype=torch.int64, device=dev) if world > 1 else None
+    # per-channel bit counts are < bins x longest codeword (2 bits) << 2^31: the report travels as int32 (16 B per channel)
+    rep_dtype = torch.int32 if T * 16 < 2 ** 31 else torch.int64
+    rep_buf = torch.empty((C_total, 4), dtype=rep_dtype, device=dev) if world > 1 else None
     # the report (bit counts, window lengths, SCLV index, peak) is complete once the encoder has run: its NCCL
     # gather goes to a side stream and overlaps the round-trip decode; the step ends when both have finished
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
@@ -221,7 +223,7 @@ def run_b200(a):
             main = torch.cuda.current_stream()
             comm.wait_stream(main)
             with torch.cuda.stream(comm):
-                rep = D.gather_channel_report(es.total_bits, en - st, ec, pk, C_total, out=rep_buf)
+                rep = D.gather_channel_report(es.total_bits, en - st, ec, pk, C_total, out=rep_buf, dtype=rep_dtype)
         P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=max_end)
         if ev: ev[3].record()
         if world > 1:

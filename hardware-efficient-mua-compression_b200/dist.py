@@ -51,12 +51,14 @@ def shard_range(C, rank, world):
     return (C * rank) // world, (C * (rank + 1)) // world
 
 
-def gather_channel_report(bits, nsym, enc, peak, C_total, group=None, out=None):
-    """All ranks receive int64 [C_total, 4] = (bits, nsym, enc, peak) in global channel order.
+def gather_channel_report(bits, nsym, enc, peak, C_total, group=None, out=None, dtype=torch.int64):
+    """All ranks receive `dtype` [C_total, 4] = (bits, nsym, enc, peak) in global channel order.
     One collective per call; with equal shards (C_total divisible by the world size) the gathered
-    buffer is returned as is -- pass `out` (int64 [C_total, 4]) to reuse it across calls."""
+    buffer is returned as is -- pass `out` (`dtype` [C_total, 4]) to reuse it across calls.
+    dtype=torch.int32 halves the bytes on the wire; the caller must know that a channel's bit count fits
+    (it does whenever bins x longest codeword < 2^31)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    local = torch.stack([bits.to(torch.int64), nsym.to(torch.int64), enc.to(torch.int64), peak.to(torch.int64)], dim=1)
+    local = torch.stack([bits.to(dtype), nsym.to(dtype), enc.to(dtype), peak.to(dtype)], dim=1)
     if world == 1:
         assert local.shape[0] == C_total
         return local
@@ -65,14 +67,14 @@ def gather_channel_report(bits, nsym, enc, peak, C_total, group=None, out=None):
     assert local.shape[0] == hi - lo, "local shard does not match shard_range()"
     if C_total % world == 0:                                # equal shards: gather straight into the result
         if out is None:
-            out = torch.empty((C_total, 4), dtype=torch.int64, device=local.device)
+            out = torch.empty((C_total, 4), dtype=dtype, device=local.device)
         dist.all_gather_into_tensor(out, local, group=group)
         return out
     sizes = [shard_range(C_total, r, world)[1] - shard_range(C_total, r, world)[0] for r in range(world)]
     m = max(sizes)
-    padded = torch.zeros((m, 4), dtype=torch.int64, device=local.device)
+    padded = torch.zeros((m, 4), dtype=dtype, device=local.device)
     padded[: local.shape[0]] = local
-    buf = torch.empty((world * m, 4), dtype=torch.int64, device=local.device)
+    buf = torch.empty((world * m, 4), dtype=dtype, device=local.device)
     dist.all_gather_into_tensor(buf, padded, group=group)
     return torch.cat([buf[r * m: r * m + sizes[r]] for r in range(world)], dim=0)
 

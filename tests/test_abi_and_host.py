@@ -83,6 +83,10 @@ assert np.array_equal(rep.numpy(), want), "gathered report differs"
 br = D.br_report(rep, 50)
 ref = np.mean(bits.astype(np.float64) / ns.astype(np.float64)) / (50 / 1000)
 assert br["BR"].tobytes() == np.float64(ref).tobytes()
+rep32 = D.gather_channel_report(torch.from_numpy(bits[lo:hi]), torch.from_numpy(ns[lo:hi]), torch.from_numpy(enc[lo:hi]),
+                                torch.from_numpy(peak[lo:hi]), C, dtype=torch.int32)          # half the bytes on the wire
+assert rep32.dtype == torch.int32 and np.array_equal(rep32.numpy(), want)
+assert D.br_report(rep32, 50)["BR"].tobytes() == np.float64(ref).tobytes()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
