@@ -3,8 +3,6 @@
 the batched kernels; channel splitting, result containers and the float64 BR arithmetic stay on the
 host in channel order, because `np.mean`/IEEE divisions are part of the bit-exact contract
 (SURVEY.md A.6)."""
-import copy
-
 import numpy as np
 import torch
 
@@ -79,7 +77,8 @@ def _br_elimination(cb, sclvs, htrain, cal, val, BP, hist_sizes):
     stored_SCLVs, stored_BRs, stored_hist = [], [], []
     while order:
         k = len(order)
-        stored_SCLVs.append(np.array(sclvs[order], dtype=object))
+        # the scripts keep the SCLV pickle's rows (float64 arrays) in an object ndarray [k, S] of Python floats (:119-124, :228)
+        stored_SCLVs.append(np.array(sclvs[order], dtype=np.float64).astype(object))
         enc_t, m1, m2 = P.select_sclv(htrain, cb, active, want_min=True)
         ah, score = P.elim_scores(enc_t, m1, m2, K)
         ah = ah.cpu().numpy()
@@ -148,12 +147,25 @@ def chosen_system(all_data_bp, S=3, H=64, BP=50, sclv=(1, 2, 2), codes=None, dev
     return BRs, detail
 
 
+def chosen_system_power(BRs, static_uW=0.96, nJ_per_bit=0.02):
+    """test_chosen_system.py:131: total power per channel in uW = 0.96 (processing) + BR x 20 nJ/bit (communication)."""
+    return static_uW + np.array(BRs) * nJ_per_bit
+
+
 def save_br_results(results, directory):
-    """Write `BRs_S_<S>_BP_<BP>_CV_<k>.pkl` files with the reference's keys and nesting
-    (get_BR_no_sort.py:324-331) so `Analyse results/` consumers keep working."""
+    """Write `BRs_S_<S>_BP_<BP>_CV_<k>.pkl` files with the reference's keys, nesting and element types
+    (get_BR_no_sort.py:324-331): `stored_all_var_BRs[round][hist][channel]` np.float64 (NaN for skipped channels),
+    `stored_SCLVs[round]` object ndarray [k, S] of floats, `stored_hist_SCLVs[round]` int64 [k],
+    `stored_val_BR_data_proportion` float64 [C_val, 9] -- what `Analyse results/integrate_BR_and_BDP_results_into_excel.py:
+    104-131` and `max_nb_channels_p_value_power_budget.py:83-93` read back.  Returns the file names written."""
     import os
     import pickle
     os.makedirs(directory, exist_ok=True)
-    for (S, BP, CV), r in results.items():
-        with open(os.path.join(directory, "BRs_S_%d_BP_%s_CV_%d.pkl" % (S, BP, CV)), "wb") as f:
-            pickle.dump(copy.copy(r), f)
+    names = []
+    for (S, BP, CV), r in sorted(results.items()):
+        name = os.path.join(directory, "BRs_S_%d_BP_%s_CV_%d.pkl" % (int(S), str(BP), int(CV)))
+        with open(name, "wb") as f:
+            pickle.dump({k: r[k] for k in ("stored_all_var_BRs", "stored_SCLVs", "stored_hist_SCLVs",
+                                           "stored_val_BR_data_proportion")}, f)
+        names.append(name)
+    return names
