@@ -40,11 +40,38 @@ def parse():
     ap.add_argument("--bins", type=int, default=72000, help="bins per channel (1 h at 50 ms)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-blocks", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="loop-time budget of the CPU baseline leg")
-    return ap.parse_args()
+    ap.add_argument("--report", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the per-channel report reaches every rank")
+    ap.add_argument("--workload", default="cfg5", choices=["cfg5", "cfg4"],
+                    help="cfg5: BASELINE configs[4], the headline (default); cfg4: one cell of the configs[3] sweep (--alphabet, --bp)")
+    ap.add_argument("--alphabet", type=int, default=5, help="cfg4: alphabet size S (3, 5, 7, 9)")
+    ap.add_argument("--bp", type=int, default=1, help="cfg4: bin period in ms (1, 10, 50); bins = 120 s / bp")
+    a = ap.parse_args()
+    if a.workload == "cfg4":
+        a.bins = 120000 // a.bp
+        if a.channels == 125000:
+            a.channels = 100000
+    return a
+
+
+def workload(a):
+    """the two bench workloads as data: alphabet, history lengths, window rule, SCLV rows, kernels of a step"""
+    if a.workload == "cfg4":
+        Sx = a.alphabet
+        kern = {3: ["k_calibrate<3>", "k_encode_fast<3>", "k_decode_lane"]}.get(Sx, ["k_calibrate<%d>" % Sx, "k_encode_pair<%d>" % Sx if Sx < 10 else "k_encode_gen", "k_decode_var"])
+        return {"name": "cfg4", "S": Sx, "BP": a.bp, "T": a.bins, "H": [2 ** e for e in range(2, 11)], "h_enc": 4, "window": "skip",
+                "sclv": None, "seed": 5, "kernels": kern,
+                "want": ("cutoff", "end", "peak", "enc", "assign_m", "post_m", "bits", "nsym")}
+    return {"name": "cfg5", "S": S, "BP": BP, "T": a.bins, "H": [H], "h_enc": 0, "window": "truncate", "sclv": np.array([SCLV]),
+            "seed": SEED, "kernels": ["k_calibrate_head<3,4>", "k_encode_fast<3>", "k_decode_lane<1>"],
+            "want": ("cutoff", "end", "peak", "enc")}
 
 
 def workload_name(a):
+    if a.workload == "cfg4":
+        return ("cfg4 cell: %d channels x %d bins (120 s at %d ms), S=%d, all SCLV rows of Stored_SCLVs_S_%d, nine history lengths "
+                "2^2..2^10 in one calibrate pass (skip rule), encode + decode at H=64, bursty Poisson" % (a.channels, a.bins, a.bp, a.alphabet, a.alphabet))
     return "cfg5 shard: %d channels x %d bins per GPU (1M-channel x 1-hour stream over 8 GPUs), S=3 H=64 BP=50ms, codebook 0/10/11, bursty Poisson" % (a.channels, a.bins)
 
 
@@ -220,11 +247,22 @@ class ClockSampler:
                 "window": "warm-up + timed steps (same load)", "reasons": sorted(reasons)}
 
 
+def _timed(fn, n):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
     import mua_b200
-    from mua_b200 import pipeline as P, dist as D
+    from mua_b200 import pipeline as P, dist as D, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -235,44 +273,79 @@ def run_b200(a):
     numa_node = D.bind_to_gpu_numa_node(local)          # host buffers of this rank on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    C, T = a.channels, a.bins
+    W = workload(a)
+    C, T, S_, BP_ = a.channels, W["T"], W["S"], W["BP"]
+    HS, h_enc = W["H"], W["h_enc"]
+    H_ = HS[h_enc]
     C_total = C * world
 
-    thr = P.synth_threshold_table(float(BP))
-    rec = P.synth_recording(C, T, seed=SEED, BP_ms=float(BP), bursty=True, c0=rank * C, device=dev, thr=thr)
-    cb = mua_b200.Codebook(S, np.array([SCLV]), device=dev)
-    # the timed path only needs the calibration window (64 samples/channel): cutoff, window end, peak, SCLV row;
-    # bit counts come out of the encoder itself
-    want = ("cutoff", "end", "peak", "enc")
-    cal = P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=want)
-    max_end = H + T // 2
+    thr = P.synth_threshold_table(float(BP_))
+    rec = P.synth_recording(C, T, seed=W["seed"], BP_ms=float(BP_), bursty=True, c0=rank * C, device=dev, thr=thr)
+    cb = mua_b200.Codebook(S_, W["sclv"], device=dev)
+    # cfg5 (the streaming system): the timed path only needs the calibration window (64 samples/channel): cutoff, window
+    # end, peak, SCLV row; bit counts come out of the encoder itself.  cfg4 (the sweep): all nine history lengths with
+    # their post-window histograms, selection and bit counts in one pass, then encode + decode at H = 64.
+    want = W["want"]
+    cal = P.calibrate(rec, cb, HS, use_sort=True, window=W["window"], want=want)
+    sel = lambda k: cal[k][:, h_enc].contiguous() if len(HS) > 1 else cal[k][:, 0]
+    max_end = H_ + T // 2
     slot = cb.worst_case_slot_bytes(T // 2 + 16)
-    es = P.encode(rec, cb, cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0], slot_bytes=slot)
+    st0, en0, pk0, ec0 = sel("cutoff"), sel("end"), sel("peak"), sel("enc")
+    es = P.encode(rec, cb, st0, en0, pk0, ec0, slot_bytes=slot)
     dec = torch.zeros_like(rec.sym)
-    # per-channel bit counts are < bins x longest codeword (2 bits) << 2^31: the report travels as int32 (16 B per channel)
+    dec_status = torch.zeros(1, dtype=torch.int32, device=dev)
+    # ---- the per-channel report (bit count, window symbols, SCLV row, peak) of all ranks on every rank ----
+    # p2p : the encoder stores every channel's 16-byte row straight into all peers' report buffers over NVLink (dist.PeerReport:
+    #       IPC-mapped peer memory, one flag per source rank); no collective, nothing left after the decode but a flag poll
+    # nccl: one all_gather_into_tensor on a side stream after the encoder (round 1)
+    report_mode, peer, peer_err = "none", None, None
+    if world > 1:
+        report_mode = a.report
+        if report_mode == "p2p" and T * cb.Lmax >= 2 ** 31:
+            report_mode = "nccl"
+        if report_mode == "p2p":
+            try:
+                peer = D.PeerReport(C, C_total)
+            except Exception as e:                       # no peer access between these GPUs: fall back, and say so
+                peer_err = repr(e)[:200]
+                peer = None
+            ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if peer is not None:
+                    peer.close()
+                    peer = None
+                report_mode = "nccl"
     rep_dtype = torch.int32 if T * 16 < 2 ** 31 else torch.int64
-    rep_buf = torch.empty((C_total, 4), dtype=rep_dtype, device=dev) if world > 1 else None
-    # the report (bit counts, window lengths, SCLV index, peak) is complete once the encoder has run: its NCCL
-    # gather goes to a side stream and overlaps the round-trip decode; the step ends when both have finished
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    rep_buf = torch.empty((C_total, 4), dtype=rep_dtype, device=dev) if report_mode == "nccl" else None
+    comm = torch.cuda.Stream(device=dev) if report_mode == "nccl" else None
     torch.cuda.synchronize()
+    step_no = [0]
+    launches_per_step = 3 + (2 if peer is not None else 0)       # k_calibrate*, k_encode*, k_decode* (+ k_report_signal, k_report_wait)
 
     def step(ev=None):
-        P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=want, out=cal)
-        st, en, pk, ec = cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0]
+        step_no[0] += 1
+        k = step_no[0]
+        P.calibrate(rec, cb, HS, use_sort=True, window=W["window"], want=want, out=cal)
+        st, en, pk, ec = sel("cutoff"), sel("end"), sel("peak"), sel("enc")
         if ev: ev[1].record()
-        P.encode(rec, cb, st, en, pk, ec, out=es)
+        P.encode(rec, cb, st, en, pk, ec, out=es, sink=peer.sink(k) if peer is not None else None)
+        if peer is not None:
+            peer.signal(k)
         if ev: ev[2].record()
         rep = None
-        if world > 1:
+        if report_mode == "nccl":
             main = torch.cuda.current_stream()
             comm.wait_stream(main)
             with torch.cuda.stream(comm):
                 rep = D.gather_channel_report(es.total_bits, en - st, ec, pk, C_total, out=rep_buf, dtype=rep_dtype)
-        P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=max_end)
+        P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=max_end, status=dec_status)
         if ev: ev[3].record()
-        if world > 1:
+        if report_mode == "nccl":
             main.wait_stream(comm)
+        elif peer is not None:
+            peer.wait(k)
+            rep = k
         if ev: ev[4].record()
         return rep
 
@@ -282,7 +355,7 @@ def run_b200(a):
         step()
         nw += 1
     torch.cuda.synchronize()
-    # ... then ~1 s under load so that the clock sampler sees it.  Every step of an N > 1 run holds a collective, so
+    # ... then ~1 s under load so that the clock sampler sees it.  Every step of an N > 1 run exchanges the report, so
     # the number of extra steps must be the same on all ranks: sized from three timed steps, MAX over ranks.
     t_w = time.perf_counter()
     for _ in range(3):
@@ -322,29 +395,49 @@ def run_b200(a):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         total_ms = float(tmax.item())
 
-    # ---- checks outside the timed region: lossless, stream length == SCLV . histogram ----
-    st, en = cal["cutoff"][:, 0], cal["end"][:, 0]
-    mism = int(P.verify(rec, dec, S, st, en).item())
+    # ---- checks outside the timed region: lossless, stream length == SCLV . histogram, the report ----
+    st, en, pk, ec = sel("cutoff"), sel("end"), sel("peak"), sel("enc")
+    mism = int(P.verify(rec, dec, S_, st, en).item())
     assert mism == 0, "decode is not lossless: %d mismatches" % mism
-    assert int(es.overflow.item()) == 0
+    assert int(es.overflow.item()) == 0 and int(dec_status.item()) == 0
     # the reference's bit count (histogram of the post window . SCLV, get_BR_no_sort.py:287) from a separate full scan
-    ref = P.calibrate(rec, cb, [H], use_sort=True, window="truncate", want=("bits", "nsym"))
+    ref = P.calibrate(rec, cb, [H_], use_sort=True, window=W["window"], want=("bits", "nsym"))
     assert torch.equal(es.total_bits, ref["bits"][:, 0]), "encoded length != SCLV . post histogram"
-    assert torch.equal(ref["nsym"][:, 0], (en - st).to(torch.int64))
+    assert torch.equal(ref["nsym"][:, 0], (en - st).clamp(min=0).to(torch.int64))
     nsym_local = int(ref["nsym"][:, 0].sum().item())
     bits_local = int(es.total_bits.sum().item())
     tot = torch.tensor([nsym_local, bits_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
     nsym_all, bits_all = int(tot[0].item()), int(tot[1].item())
-    if rep is None:
-        rep = D.gather_channel_report(es.total_bits, en - st, cal["enc"][:, 0], cal["peak"][:, 0], C_total)
-    br = D.br_report(rep, BP) if rank == 0 else None
+    local_rep = torch.stack([es.total_bits, (en - st).clamp(min=0).to(torch.int64), ec.to(torch.int64), pk.to(torch.int64)], dim=1)
+    report_verified = None
+    if world == 1:
+        rep_t = local_rep
+    else:
+        if peer is not None:
+            assert not peer.timed_out(), "a peer's report rows never arrived"
+            rep_t = peer.report(rep).clone()
+        else:
+            rep_t = rep
+        lo, hi = D.shard_range(C_total, rank, world)
+        assert torch.equal(rep_t[lo:hi].to(torch.int64), local_rep), "gathered report != local slice"
+        # identical on every rank: position-weighted checksums, MIN and MAX over ranks must agree
+        w = torch.arange(1, C_total + 1, dtype=torch.int64, device=dev)
+        r64 = rep_t.to(torch.int64)
+        chk = torch.stack([(r64[:, j] * w).sum() for j in range(4)] + [r64.sum()])
+        cmin, cmax = chk.clone(), chk.clone()
+        dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+        assert torch.equal(cmin, cmax), "the gathered report differs between ranks"
+        assert int(r64[:, 0].sum().item()) == bits_all and int(r64[:, 1].sum().item()) == nsym_all
+        report_verified = True
+    br = D.br_report(rep_t, BP_) if rank == 0 else None
 
     ms_per_step = total_ms / a.steps
     value = nsym_all / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (encode vs decode), algorithmic bytes per launch ----
+    # ---- roofline of the dominant kernel, algorithmic bytes per launch ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak_gbs, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -354,100 +447,173 @@ def run_b200(a):
     side = 4 * n_chunks + 8 * C
     enc_bytes = nsym_local + bits_local / 8 + side            # symbols read + stream written + side info
     dec_bytes = bits_local / 8 + nsym_local + 4 * n_chunks    # stream read + symbols written + offsets read
+    cal_bytes = float(C) * min(T, (max(HS) + T // 2) if W["name"] == "cfg4" else H_)   # bins scanned by the calibrate pass
     stages = {"calibrate_ms": float(stage_ms[0]), "encode_ms": float(stage_ms[1]), "decode_ms": float(stage_ms[2]),
-              "gather_ms": float(stage_ms[3]),   # N > 1: what is left of the NCCL gather after the decode it overlaps
-
+              "gather_ms": float(stage_ms[3]),   # N > 1: what is left of the report exchange after the decode it overlaps
+              "calibrate_gbs": cal_bytes / stage_ms[0] / 1e6, "calibrate_frac": cal_bytes / stage_ms[0] / 1e6 / peak_gbs,
               "encode_gbs": enc_bytes / stage_ms[1] / 1e6, "decode_gbs": dec_bytes / stage_ms[2] / 1e6,
               "encode_frac": enc_bytes / stage_ms[1] / 1e6 / peak_gbs, "decode_frac": dec_bytes / stage_ms[2] / 1e6 / peak_gbs,
               "combined_gbs": (enc_bytes + dec_bytes) / (stage_ms[1] + stage_ms[2]) / 1e6,
               "combined_frac": (enc_bytes + dec_bytes) / (stage_ms[1] + stage_ms[2]) / 1e6 / peak_gbs,
               "bits_per_symbol": bits_local / max(nsym_local, 1)}
-    dom = "k_encode" if stage_ms[1] >= stage_ms[2] else "k_decode"
-    ach = stages["encode_gbs"] if dom == "k_encode" else stages["decode_gbs"]
+    names = W["kernels"]
+    order = np.argsort([-stage_ms[0], -stage_ms[1], -stage_ms[2]])
+    di = int(order[0])
+    dom = names[di]
+    ach = [stages["calibrate_gbs"], stages["encode_gbs"], stages["decode_gbs"]][di]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("channels") == C and tj.get("bins") == T:
-            traffic = tj.get(dom)
+        key = ["k_calibrate", "k_encode", "k_decode"][di]
+        if tj.get("channels") == C and tj.get("bins") == T and tj.get("workload", "cfg5") == W["name"]:
+            traffic = tj.get(key)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                 "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": enc_bytes if dom == "k_encode" else dec_bytes}
+                "algorithmic_bytes_per_launch": [cal_bytes, enc_bytes, dec_bytes][di]}
 
-    # ---- e2e: host buffers in, compressed streams + report out, chunked over 3 CUDA streams ----
+    # ---- e2e: host buffers in, compressed streams + report out ----
     e2e = None
     if not a.no_e2e:
-        e2e = run_e2e(a, rec, cb, dev, world, rank)
+        e2e = run_e2e(a, W, rec, cb, dev, world, rank)
 
-    cpu = cpu_baseline_single(T, budget_s=a.cpu_seconds) if rank == 0 else None
+    cpu = cpu_baseline_single(T, budget_s=a.cpu_seconds) if (rank == 0 and W["name"] == "cfg5") else None
     if rank == 0:
+        cfg = config_dict(a, world)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "warmup_steps_run": nw, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": workload_name(a), "channels_per_gpu": C, "bins": T, "total_channels": C_total,
-                       "l2": "inputs (%.1f GB per GPU) are larger than L2" % (C * T / 1e9), "sharding": "channels, contiguous blocks"},
-            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * a.steps,
+            "data": "synthetic", "config": cfg,
+            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * a.steps,
+            "launches_per_step": {"own_kernels": launches_per_step, "kernels": names + (["k_report_signal", "k_report_wait"] if peer is not None else []),
+                                  "other": "none" if report_mode != "nccl" else "torch stack/cast kernels + NCCL all_gather on the side stream"},
+            "report": {"mode": report_mode, "verified": report_verified, "fallback_reason": peer_err,
+                       "what": {"p2p": "rows stored by the encoder into every peer's buffer over NVLink, flag poll after the decode",
+                                "nccl": "all_gather_into_tensor on a side stream", "none": "single GPU"}[report_mode]},
+            "report_verified": report_verified,
             "clocks": clocks, "BR_bits_per_s_per_channel": float(br["BR"]), "lossless": True,
             "symbols_per_step": nsym_all, "numa_node_rank0": numa_node}))
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(a, rec, cb, dev, world, rank):
-    """Same metric through the public API with HOST buffers: every step moves the whole shard from pinned
-    host memory to the device in channel blocks, runs calibrate/encode/decode on each block, and reads
-    the compressed streams and the per-channel report back to pinned host memory.  Blocks rotate over
-    3 CUDA streams so copies overlap compute.  To keep the pinned footprint at ~1/10 of the shard, the
-    host side holds ONE block of the synthetic stream and every block of a step is copied from it (the
-    bytes moved per step are those of the full shard)."""
+def run_e2e(a, W, rec, cb, dev, world, rank):
+    """Same metric through the public API with HOST buffers.  The host owns this rank's WHOLE shard in pinned memory (the bins
+    the path reads: [0, H + T//2) of every row).  Every step moves it to the device in channel blocks over `nstream` CUDA
+    streams, runs calibrate / encode / decode on each block, packs the used part of the streams densely on the device
+    (mua_pack_streams) and reads the dense streams, their offsets and the per-channel report back to pinned host memory.
+    The dense size is only known on the device, so the read-back of block i is enqueued once the (tiny) offsets copy of that
+    block has completed -- two blocks later in the loop, so the host never waits on the block it has just enqueued."""
     import torch
     import torch.distributed as dist
     from mua_b200 import pipeline as P
-    C, T = a.channels, a.bins
-    nblk = max(1, min(10, C // 1000))
-    nb = C // nblk                                          # channels per block (a remainder is folded into the count)
-    nblk_eff = (C + nb - 1) // nb
-    h_in = torch.empty((nb, rec.stride), dtype=torch.uint8, pin_memory=True)
-    h_in.copy_(rec.sym[:nb])                               # setup: the host owns the input
+    C, T, S_ = a.channels, W["T"], W["S"]
+    HS, h_enc = W["H"], W["h_enc"]
+    H_ = HS[h_enc]
+    nblk = max(1, min(a.e2e_blocks, C // 1000)) if C >= 1000 else 1
+    nb = (C + nblk - 1) // nblk                             # channels per block (the last block may be shorter)
+    nblk = (C + nb - 1) // nb
+    nstream = 4
     slot = cb.worst_case_slot_bytes(T // 2 + 16)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
-    want = ("cutoff", "end", "peak", "enc")
-    max_end = H + T // 2
+    want = W["want"]
+    max_end = H_ + T // 2
     need = min(rec.stride, (max_end + 15) // 16 * 16)      # bytes of every row the path reads
+    sel = lambda cal, k: cal[k][:, h_enc].contiguous() if len(HS) > 1 else cal[k][:, 0]
+    # ---- setup (untimed): the host's copy of the shard, per-stream device and host buffers ----
+    h_in = torch.empty((C, need), dtype=torch.uint8, pin_memory=True)
+    for i in range(nblk):
+        h_in[i * nb:(i + 1) * nb].copy_(rec.sym[i * nb:(i + 1) * nb, :need])
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstream)]
     bufs = []
     for s in streams:
         with torch.cuda.stream(s):
-            r = P.Recording(sym=torch.empty((nb, rec.stride), dtype=torch.uint8, device=dev), C=nb, T=T, stride=rec.stride)
-            r.sym.copy_(h_in, non_blocking=True)
-            cal = P.calibrate(r, cb, [H], use_sort=True, window="truncate", want=want)
-            es = P.encode(r, cb, cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0], slot_bytes=slot)
-            dec = torch.zeros_like(r.sym)
-            repd = torch.empty((nb, 2), dtype=torch.int64, device=dev)
-            h_stream = torch.empty((nb, slot), dtype=torch.uint8, pin_memory=True)
-            h_rep = torch.empty((nb, 2), dtype=torch.int64, pin_memory=True)
-            bufs.append((r, cal, es, dec, repd, h_stream, h_rep))
+            r = P.Recording(sym=torch.zeros((nb, rec.stride), dtype=torch.uint8, device=dev), C=nb, T=T, stride=rec.stride)
+            r.upload_rows(h_in[:nb], need)
+            cal = P.calibrate(r, cb, HS, use_sort=True, window=W["window"], want=want)
+            es = P.encode(r, cb, sel(cal, "cutoff"), sel(cal, "end"), sel(cal, "peak"), sel(cal, "enc"), slot_bytes=slot)
+            bufs.append({"rec": r, "cal": cal, "es": es, "dec": torch.zeros_like(r.sym),
+                         "dense": torch.empty(nb * slot, dtype=torch.uint8, device=dev),
+                         "uoff": torch.empty(nb + 1, dtype=torch.int64, device=dev),
+                         "rep": torch.empty((nb, 2), dtype=torch.int64, device=dev),
+                         "status": torch.zeros(1, dtype=torch.int32, device=dev),
+                         "h_dense": torch.empty(nb * slot, dtype=torch.uint8, pin_memory=True),
+                         "h_uoff": torch.empty(nb + 1, dtype=torch.int64, pin_memory=True),
+                         "h_rep": torch.empty((nb, 2), dtype=torch.int64, pin_memory=True),
+                         "ev": torch.cuda.Event(), "done": torch.cuda.Event()})
     torch.cuda.synchronize()
+    acct = {"d2h": 0, "nsym": 0, "bits": 0}
+
+    def finish(i):
+        """block i's offsets have been copied: enqueue the read-back of exactly its dense bytes"""
+        b, s = bufs[i % nstream], streams[i % nstream]
+        b["ev"].synchronize()
+        nbytes = int(b["h_uoff"][-1 if (i + 1) * nb <= C else C - i * nb]) * 16
+        with torch.cuda.stream(s):
+            b["h_dense"][:nbytes].copy_(b["dense"][:nbytes], non_blocking=True)
+            b["done"].record(s)
+        acct["d2h"] += nbytes + b["h_uoff"].numel() * 8 + b["h_rep"].numel() * 8
+        n_i = min(nb, C - i * nb)
+        acct["nsym"] += int(b["h_rep"][:n_i, 1].sum())
+        acct["bits"] += int(b["h_rep"][:n_i, 0].sum())
 
     def one_step():
-        for i in range(nblk_eff):
-            s = streams[i % 3]
-            r, cal, es, dec, repd, h_stream, h_rep = bufs[i % 3]
+        acct["d2h"] = acct["nsym"] = acct["bits"] = 0
+        lag = nstream - 2
+        for i in range(nblk):
+            if i >= nstream:
+                bufs[i % nstream]["done"].synchronize()          # the host buffers of this slot have been read back
+            b, s = bufs[i % nstream], streams[i % nstream]
+            n_i = min(nb, C - i * nb)
             with torch.cuda.stream(s):
-                r.upload_rows(h_in, need)                       # only the bins the path reads: [0, H + T//2)
-                P.calibrate(r, cb, [H], use_sort=True, window="truncate", want=want, out=cal)
-                st, en, pk, ec = cal["cutoff"][:, 0], cal["end"][:, 0], cal["peak"][:, 0], cal["enc"][:, 0]
+                r, cal, es = b["rec"], b["cal"], b["es"]
+                r.upload_rows(h_in[i * nb:i * nb + n_i], need)   # only the bins the path reads: [0, H + T//2)
+                P.calibrate(r, cb, HS, use_sort=True, window=W["window"], want=want, out=cal)
+                st, en, pk, ec = sel(cal, "cutoff"), sel(cal, "end"), sel(cal, "peak"), sel(cal, "enc")
                 P.encode(r, cb, st, en, pk, ec, out=es)
-                P.decode(es, r, cb, st, en, pk, ec, out=dec, max_end=max_end)
-                repd[:, 0] = es.total_bits
-                repd[:, 1] = en - st
-                h_stream.copy_(es.stream, non_blocking=True)
-                h_rep.copy_(repd, non_blocking=True)
+                P.decode(es, r, cb, st, en, pk, ec, out=b["dec"], max_end=max_end, status=b["status"])
+                P.pack_streams(es, b["dense"], b["uoff"])
+                b["rep"][:, 0] = es.total_bits
+                b["rep"][:, 1] = (en - st).clamp(min=0)
+                b["h_uoff"].copy_(b["uoff"], non_blocking=True)
+                b["h_rep"].copy_(b["rep"], non_blocking=True)
+                b["ev"].record(s)
+            if i >= lag:
+                finish(i - lag)
+        for i in range(max(nblk - lag, 0), nblk):
+            finish(i)
         for s in streams:
             s.synchronize()
 
     one_step()
     torch.cuda.synchronize()
+    assert all(int(b["status"].item()) == 0 and int(b["es"].overflow.item()) == 0 for b in bufs)
+    # spot check of the read-back: block 0's first stream equals the slot it was packed from
+    # ---- concurrent host->device probe: what the host side gives each rank when all ranks copy at once ----
+    probe = None
+    if world > 1 or True:
+        tgt = torch.empty((nb, need), dtype=torch.uint8, device=dev)
+        def h2d_all():
+            for i in range(nblk):
+                n_i = min(nb, C - i * nb)
+                tgt[:n_i].copy_(h_in[i * nb:i * nb + n_i], non_blocking=True)
+        h2d_all(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_p = _timed(h2d_all, 1)
+        mine = h_in.numel() / ms_p / 1e6
+        if world > 1:
+            allv = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allv, torch.tensor([mine], dtype=torch.float64, device=dev))
+            per_rank = [float(v.item()) for v in allv]
+        else:
+            per_rank = [mine]
+        probe = {"per_rank_gbs": [round(v, 2) for v in per_rank], "aggregate_gbs": round(sum(per_rank), 2),
+                 "what": "every rank copies its whole pinned shard (%d x %d B) host->device at the same time, plain cudaMemcpyAsync, "
+                         "nothing else running" % (C, need)}
+        del tgt
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -459,20 +625,30 @@ def run_e2e(a, rec, cb, dev, world, rank):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.e2e_steps
     wall_ms = (time.perf_counter() - t0) * 1e3 / a.e2e_steps
-    ms = max(ms, wall_ms)
+    ms_own = max(ms, wall_ms)
+    ms = ms_own
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    nsym = int(bufs[0][6][:, 1].sum().item()) * nblk_eff
-    tot = torch.tensor([nsym], dtype=torch.int64, device=dev)
+    tot = torch.tensor([acct["nsym"], acct["d2h"], int(h_in.numel())], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
-    return {"value": int(tot.item()) / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nblk_eff * nb * need),
-            "d2h_bytes_per_step": int(nblk_eff * nb * (slot + 16)), "ms_per_step": ms, "steps": a.e2e_steps,
-            "api": "mua_b200.pipeline.calibrate/encode/decode (C ABI) on pinned host buffers, %d channel blocks of %d channels over "
-                   "3 CUDA streams; only bins [0, H + T//2) of every row are uploaded (all the path reads); all blocks are copied "
-                   "from one pinned block of the synthetic stream" % (nblk_eff, nb)}
+    nsym_all = int(tot[0].item())
+    h2d_rate = h_in.numel() / ms_own / 1e6
+    ceiling = None
+    if probe:
+        # if the host->device copies were the only thing in a step: symbols / (bytes / the slowest rank's concurrent copy rate)
+        ceiling = nsym_all / (h_in.numel() / (min(probe["per_rank_gbs"]) * 1e9))
+    return {"value": nsym_all / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(tot[2].item()),
+            "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": ms, "steps": a.e2e_steps,
+            "h2d_gbs_this_rank": round(h2d_rate, 2), "h2d_probe": probe, "h2d_only_ceiling": ceiling,
+            "frac_of_h2d_ceiling": (nsym_all / (ms * 1e-3)) / ceiling if ceiling else None,
+            "pinned_host_bytes_per_rank": int(h_in.numel()),
+            "api": "mua_b200.pipeline.calibrate/encode/decode/pack_streams (C ABI) on pinned host buffers holding the rank's whole shard, "
+                   "%d channel blocks of %d channels over %d CUDA streams; only bins [0, H + T//2) of every row are uploaded (all the "
+                   "path reads); read back: the dense streams (ceil(bits/128)*16 B per channel), their offsets and the per-channel report"
+                   % (nblk, nb, nstream)}
 
 
 def _protect_stdout():

@@ -11,6 +11,9 @@ WINDOW_NONE, WINDOW_SKIP, WINDOW_TRUNCATE = 0, 1, 2
 DT_U8, DT_I32, DT_I64, DT_F32, DT_F64 = 0, 1, 2, 3, 4
 CHUNK = 1024
 MAX_H = 16
+ABI_VERSION = 2
+ENC_OVERFLOW, ENC_BAD_TABLE = 1, 2          # *d_overflow of mua_encode
+DEC_BAD_OFFSET, DEC_BAD_TABLE = 1, 2         # *d_status of mua_decode
 
 _vp, _i32, _i64, _u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
 
@@ -19,6 +22,15 @@ class CalibOut(C.Structure):
     _fields_ = [("S", _i32), ("d_tables", _vp), ("active_lo", _u32), ("active_hi", _u32),
                 ("d_cutoff", _vp), ("d_end", _vp), ("d_peak", _vp), ("d_enc", _vp), ("d_assign_m", _vp),
                 ("d_post_m", _vp), ("d_bits", _vp), ("d_nsym", _vp), ("d_train_hist", _vp)]
+
+
+MAX_PEERS = 16
+IPC_HANDLE_BYTES = 64
+
+
+class ReportSink(C.Structure):
+    """struct mua_report_sink (include/mua_b200.h): every peer's report buffer and flag block."""
+    _fields_ = [("n_peers", _i32), ("rank", _i32), ("row0", _i64), ("d_report", _vp * MAX_PEERS), ("d_flags", _vp * MAX_PEERS)]
 
 
 #: every symbol include/mua_b200.h declares -> (restype, argtypes)
@@ -39,9 +51,16 @@ SIGNATURES = {
     "mua_bit_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mua_elim_scores": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mua_encode": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                             _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+                             _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mua_pack_streams": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "mua_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), _vp]),
+    "mua_peer_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "mua_peer_close": (C.c_int, [_vp]),
+    "mua_peer_free": (C.c_int, [_vp]),
+    "mua_report_signal": (C.c_int, [_vp, _i32, _vp]),
+    "mua_report_wait": (C.c_int, [_vp, _i32, _vp]),
     "mua_decode": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                             _i32, _vp, _vp]),
+                             _i32, _vp, _vp, _vp]),
     "mua_verify": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mua_online_histogram": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "mua_approx_sort": (C.c_int, [_vp, C.c_int, _i32, _i64, _vp, _vp]),
@@ -69,7 +88,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.mua_abi_version() != 1:
+    if lib.mua_abi_version() != ABI_VERSION:
         raise MuaError("libmua_b200.so ABI version mismatch")
     _lib = lib
     return lib

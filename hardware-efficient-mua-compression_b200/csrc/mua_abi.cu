@@ -394,10 +394,84 @@ int mua_elim_scores(const uint8_t* d_enc, const int64_t* d_min1, const int64_t* 
     return MUA_OK;
 }
 
+int mua_peer_alloc(size_t bytes, void** d_ptr, uint8_t* h_handle) {
+    REQUIRE(d_ptr && h_handle && bytes > 0, "NULL argument / zero size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MUA_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (peer buffer)");
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    memcpy(h_handle, &h, sizeof(h));
+    *d_ptr = p;
+    return MUA_OK;
+}
+
+int mua_peer_open(const uint8_t* h_handle, void** d_ptr) {
+    REQUIRE(d_ptr && h_handle, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    *d_ptr = p;
+    return MUA_OK;
+}
+
+int mua_peer_close(void* d_ptr) {
+    if (!d_ptr) return MUA_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+    return e == cudaSuccess ? MUA_OK : cuda_fail(e, "cudaIpcCloseMemHandle");
+}
+
+int mua_peer_free(void* d_ptr) {
+    if (!d_ptr) return MUA_OK;
+    cudaError_t e = cudaFree(d_ptr);
+    return e == cudaSuccess ? MUA_OK : cuda_fail(e, "cudaFree (peer buffer)");
+}
+
+static int check_sink(const mua_report_sink* s) {
+    REQUIRE(s, "report sink is NULL");
+    REQUIRE(s->n_peers >= 1 && s->n_peers <= MUA_MAX_PEERS && s->rank >= 0 && s->rank < s->n_peers, "bad report sink ranks");
+    for (int i = 0; i < s->n_peers; ++i) REQUIRE(s->d_flags[i], "report sink: d_flags[%d] is NULL", i);
+    return MUA_OK;
+}
+
+int mua_report_signal(const mua_report_sink* h_sink, int32_t step, void* stream) {
+    int rc = check_sink(h_sink);
+    if (rc) return rc;
+    PeerFlags F;
+    F.n = h_sink->n_peers; F.rank = h_sink->rank;
+    for (int i = 0; i < MUA_MAX_PEERS; ++i) F.flags[i] = i < F.n ? h_sink->d_flags[i] : nullptr;
+    k_report_signal<<<1, 32, 0, (cudaStream_t)stream>>>(F, step);
+    CHECK_LAUNCH("k_report_signal");
+    return MUA_OK;
+}
+
+int mua_report_wait(const mua_report_sink* h_sink, int32_t step, void* stream) {
+    int rc = check_sink(h_sink);
+    if (rc) return rc;
+    int khz = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    PeerFlags F;
+    F.n = h_sink->n_peers; F.rank = h_sink->rank;
+    for (int i = 0; i < MUA_MAX_PEERS; ++i) F.flags[i] = i < F.n ? h_sink->d_flags[i] : nullptr;
+    k_report_wait<<<1, 32, 0, (cudaStream_t)stream>>>(F, step, (long long)(khz > 0 ? khz : 1500000) * 2000ll);
+    CHECK_LAUNCH("k_report_wait");
+    return MUA_OK;
+}
+
 int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C, int32_t S,
                const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak, const uint8_t* d_enc, const void* d_tables,
                int32_t K, int32_t Lmax, uint8_t* d_stream, int64_t slot_bytes, uint32_t* d_chunk_off, int32_t chunk_stride,
-               int64_t* d_total_bits, int32_t* d_overflow, void* stream) {
+               int64_t* d_total_bits, int32_t* d_overflow, const mua_report_sink* h_sink, void* stream) {
     int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
     if (rc) return rc;
     if (C == 0) return MUA_OK;                                  // nothing to encode: per-channel arrays may be empty (NULL)
@@ -415,6 +489,18 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax;
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
     P.total_bits = d_total_bits; P.overflow = d_overflow;
+    P.n_peers = 0; P.row0 = 0;
+    for (int i = 0; i < MUA_MAX_PEERS; ++i) P.rep[i] = nullptr;
+    if (h_sink && h_sink->n_peers > 0) {
+        REQUIRE(h_sink->n_peers <= MUA_MAX_PEERS && h_sink->row0 >= 0, "bad report sink");
+        REQUIRE((long long)T * Lmax < (1ll << 31), "report sink rows are int32: T * Lmax must be < 2^31");
+        for (int i = 0; i < h_sink->n_peers; ++i) {
+            REQUIRE(h_sink->d_report[i] && aligned16(h_sink->d_report[i]), "report sink: d_report[%d] NULL or not 16-byte aligned", i);
+            P.rep[i] = h_sink->d_report[i];
+        }
+        P.n_peers = h_sink->n_peers;
+        P.row0 = h_sink->row0;
+    }
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
     if (h.Lmax <= 2 && S <= 4) {
         const int smem = EncFastSmem::PER_WARP * EF_WARPS;
@@ -461,12 +547,34 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     return MUA_OK;
 }
 
+int mua_pack_streams(const uint8_t* d_stream, int64_t slot_bytes, const int64_t* d_total_bits, int32_t C, int64_t* d_unit_off,
+                     uint8_t* d_dense, int64_t dense_bytes, void* stream) {
+    REQUIRE(C >= 0, "C < 0");
+    REQUIRE(d_unit_off, "d_unit_off is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 0) {
+        cudaError_t e = cudaMemsetAsync(d_unit_off, 0, sizeof(int64_t), st);
+        return e == cudaSuccess ? MUA_OK : cuda_fail(e, "memset");
+    }
+    REQUIRE(d_stream && d_total_bits && d_dense, "NULL argument");
+    REQUIRE(aligned16(d_stream) && aligned16(d_dense) && slot_bytes > 0 && slot_bytes % 16 == 0 && dense_bytes >= 0,
+            "d_stream/d_dense/slot_bytes must be 16-byte aligned");
+    k_pack_offsets<<<1, 1024, 0, st>>>(d_total_bits, C, slot_bytes >> 4, d_unit_off);
+    CHECK_LAUNCH("k_pack_offsets");
+    const int need = (C + 7) / 8;
+    const int grid = need < sm_count() * 8 ? need : sm_count() * 8;
+    k_pack_copy<<<grid, 256, 0, st>>>(d_stream, slot_bytes, C, d_unit_off, d_dense, dense_bytes >> 4);
+    CHECK_LAUNCH("k_pack_copy");
+    return MUA_OK;
+}
+
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off, int32_t chunk_stride, const int64_t* d_off,
                int64_t stride, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
-               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end, uint8_t* d_dec, void* stream) {
+               const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end, uint8_t* d_dec,
+               int32_t* d_status, void* stream) {
     REQUIRE(C >= 0, "C < 0");
     if (C == 0) return MUA_OK;                                  // nothing to decode: per-channel arrays may be empty (NULL)
-    REQUIRE(d_stream && d_chunk_off && d_start && d_end && d_peak && d_enc && d_tables && d_dec, "NULL argument");
+    REQUIRE(d_stream && d_chunk_off && d_start && d_end && d_peak && d_enc && d_tables && d_dec && d_status, "NULL argument");
     REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
     REQUIRE(aligned16(d_dec), "d_dec must be 16-byte aligned");
     REQUIRE(d_off || stride % 16 == 0, "stride must be a multiple of 16");
@@ -479,7 +587,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     DecParams P;
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
     P.off = d_off; P.stride = stride; P.C = C; P.S = S; P.start = d_start; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
-    P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax; P.dec = d_dec;
+    P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax; P.dec = d_dec; P.status = d_status;
     REQUIRE(slot_bytes < (1ll << 32), "slot_bytes must be < 4 GiB");
     // chunks per channel that can be non-empty: ceil(max_end / CHUNK) when the caller bounds the window end
     P.item_chunks = chunk_stride;
@@ -492,9 +600,6 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
         if (h.K <= DL_MAX_ROWS && h.S <= 8 && h.W == 8) {   // lane-private LUT banks: one persistent CTA per SM
 #ifndef MUA_DL_NC
 #define MUA_DL_NC 1
-#endif
-#ifndef MUA_DECODE_VAR
-#define MUA_DECODE_VAR 1
 #endif
 #ifndef MUA_DV_PPS
 #define MUA_DV_PPS 1          // 128-symbol periods per staged stream row of k_decode_var
@@ -523,7 +628,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
             k_decode_fast<false><<<grid, DF_WARPS * 32, smem, st>>>(P);
         }
-    } else if (MUA_DECODE_VAR && h.decv_off) {
+    } else {
         // variable-count lookups from per-row rank tables in shared memory: one persistent CTA per SM
         const int fixed = 4 * MUA_MAX_S * 4 + 16 + (h.K << h.Wv) * 4;      // rank maps, ticket, tables
         P.var_pps = MUA_DV_PPS;
@@ -544,21 +649,6 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
             k_decode_var<false><<<grid, nw * 32, smem, st>>>(P);
         }
-    } else {
-        const int smem = DG_WARPS * DG_PER_WARP + (smem_lut ? lut_bytes : 0);
-        const long long blocks_needed = (groups + DG_WARPS - 1) / DG_WARPS;
-        const long long cap = (long long)sm_count() * 4;
-        const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
-#define MUA_LAUNCH_DEC(NS, SL)                                                                                            \
-    do {                                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(k_decode_gen<NS, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
-        if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");                                              \
-        k_decode_gen<NS, SL><<<grid, DG_WARPS * 32, smem, st>>>(P);                                                      \
-    } while (0)
-        if (h.nsym == 4) { if (smem_lut) MUA_LAUNCH_DEC(4, true); else MUA_LAUNCH_DEC(4, false); }
-        else if (h.nsym == 2) { if (smem_lut) MUA_LAUNCH_DEC(2, true); else MUA_LAUNCH_DEC(2, false); }
-        else { if (smem_lut) MUA_LAUNCH_DEC(1, true); else MUA_LAUNCH_DEC(1, false); }
-#undef MUA_LAUNCH_DEC
     }
     CHECK_LAUNCH("k_decode");
     return MUA_OK;

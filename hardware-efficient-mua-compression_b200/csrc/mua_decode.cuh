@@ -21,173 +21,30 @@ struct DecParams {
     const uint8_t* tab;
     int32_t K, Lmax;
     uint8_t* dec;
+    int32_t* status;            // see dec_flag
     int32_t var_str_w, var_pps;   // k_decode_var: staged stream words per lane and stage, 128-symbol periods per stage
 };
 
-// ---- general decoder (any codebook) ----
-// One lane decodes one 1024-symbol chunk; a warp owns 32 consecutive chunks.
-//   * the lanes' stream bytes are staged into shared memory by the whole warp with coalesced 16-byte
-//     loads (272 B per lane and stage, byte-swapped to MSB-first words on the way in);
-//   * every LUT lookup decodes exactly NSYM symbols (window W = NSYM*Lmax bits), so output words are
-//     produced at fixed positions -- no variable-length output assembly;
-//   * decoded symbols go to a padded shared-memory tile (128 B per lane and period) that the warp
-//     writes out with coalesced 16-byte stores.
-constexpr int DG_WARPS = 4;
-constexpr int DG_STR_W = 68;          // staged stream words per lane: 272 B = 128 bits of alignment slack + 2048 bits
-constexpr int DG_OUT_B = 144;         // output tile row: 128 B + 16 B pad
-constexpr int DG_PER_WARP = 32 * DG_STR_W * 4 + 32 * DG_OUT_B + 16;   // + mbarrier
+constexpr int DG_OUT_B = 144;         // output tile row of the general decoder: 128 B + 16 B pad
 
-template <int NSYM, bool SMEM_LUT>
-__global__ void __launch_bounds__(DG_WARPS * 32, 3) k_decode_gen(const __grid_constant__ DecParams P) {
-    extern __shared__ __align__(128) uint8_t dsm[];
-    const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
-    const int K = T->K, W = T->W;
-    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != NSYM) return;   // host view does not match the table block
-    const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* s_str = reinterpret_cast<uint32_t*>(dsm + warp * DG_PER_WARP);
-    uint8_t* s_out = dsm + warp * DG_PER_WARP + 32 * DG_STR_W * 4;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + 32 * DG_OUT_B);
-    const uint32_t* s_lut = reinterpret_cast<const uint32_t*>(dsm + DG_WARPS * DG_PER_WARP);
-    if (lane == 0) {
-        mbar_init(s_bar, 1);
-        fence_barrier_init();
-    }
-    if (SMEM_LUT) {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(dsm + DG_WARPS * DG_PER_WARP);
-        const int nent = (T->S * K) << W;
-        for (int i = threadIdx.x; i < nent; i += blockDim.x) dst[i] = g_lut[i];
-    }
-    __syncthreads();
-    uint32_t parity = 0;
-    const int periods_per_stage = 2048 / (128 * T->Lmax);        // 128-symbol periods one staged row is good for
-    const long long nitems = (long long)P.C * P.item_chunks;
-    const long long ngroups = (nitems + 31) / 32;
-    const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
-
-    for (long long g = (long long)blockIdx.x * DG_WARPS + warp; g < ngroups; g += (long long)gridDim.x * DG_WARPS) {
-        // ---- this lane's chunk ----
-        const long long item = g * 32 + lane;
-        int rem = 0;
-        uint32_t bitpos = 0;
-        const uint8_t* sbase = P.stream;
-        uint8_t* optr = P.dec;
-        const uint32_t* lut = SMEM_LUT ? s_lut : g_lut;
-        if (item < nitems) {
-            const int c = (int)(item / P.item_chunks), j = (int)(item % P.item_chunks);
-            const int start = P.start[c], end = P.end[c];
-            if (end > start && start >= 0) {
-                const int j0 = start / TILE;
-                const int nch = (end + TILE - 1) / TILE - j0;
-                if (j < nch) {
-                    const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
-                    rem = b - a;
-                    bitpos = P.chunk_off[(size_t)c * P.chunk_stride + j];
-                    sbase = P.stream + (size_t)c * P.slot_bytes;
-                    optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
-                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W;
-                }
-            }
-        }
-        int done = 0;                                            // symbols already written out
-        while (__any_sync(FULL, rem > 0)) {
-            // ---- stage 272 stream bytes per lane (one TMA bulk copy each), from the 16-byte unit holding `bitpos` ----
-            const uint32_t cur_al = (bitpos >> 7) << 4;
-            const uint32_t nbytes = rem > 0 ? min((uint32_t)(DG_STR_W * 4), slot_bytes - cur_al) : 0u;
-            const uint32_t total = __reduce_add_sync(FULL, nbytes);
-            __syncwarp();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (total) {
-                if (lane == 0) mbar_expect_tx(s_bar, total);
-                __syncwarp();
-                if (nbytes) tma_load_1d(s_str + lane * DG_STR_W, sbase + cur_al, nbytes, s_bar);
-                mbar_wait(s_bar, parity);
-                parity ^= 1;
-            }
-            const uint32_t* rowp = s_str + lane * DG_STR_W;
-            const uint32_t boff = bitpos - cur_al * 8;           // 0..127
-            uint32_t rp = boff >> 5;
-            uint32_t hi = bswap32(rowp[rp]), lo = bswap32(rowp[rp + 1]);
-            rp += 2;
-            uint32_t off = boff & 31;
-            uint32_t consumed = 0;                               // bits consumed in this stage
-
-            for (int per = 0; per < periods_per_stage && __any_sync(FULL, rem > 0); ++per) {
-                // ---- 128 symbols per lane into the output tile ----
-                uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DG_OUT_B);
-#pragma unroll 2
-                for (int q = 0; q < 8; ++q) {
-                    uint32_t ow[4];
-                    if (NSYM == 4) {
-                        // one 32-bit snapshot feeds 4 lookups of <= 8 bits; refill check once per 16 symbols
-                        const uint32_t x = __funnelshift_l(lo, hi, off);
-                        uint32_t o = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t e = lut[(x << o) >> (32 - W)];
-                            ow[k] = e & 0x0F0F0F0Fu;
-                            o += e >> 28;
-                        }
-                        off += o;
-                        consumed += o;
-                        if (off >= 32) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(DG_STR_W - 1))]); ++rp; off -= 32; }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            uint32_t wsym = 0;
-#pragma unroll
-                            for (int h = 0; h < 4 / NSYM; ++h) {
-                                const uint32_t x = __funnelshift_l(lo, hi, off);
-                                const uint32_t e = lut[x >> (32 - W)];
-                                wsym |= (e & 0x0F0F0F0Fu) << (8 * NSYM * h);
-                                const uint32_t used = e >> 28;
-                                off += used;
-                                consumed += used;
-                                if (off >= 32) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(DG_STR_W - 1))]); ++rp; off -= 32; }
-                            }
-                            ow[k] = wsym;
-                        }
-                    }
-                    orow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                }
-                __syncwarp();
-                // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
-                const int vrow_self = min(max(rem, 0), 128);     // valid bytes of my row in this period
-#pragma unroll 1
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + (lane >> 3), col = lane & 7;
-                    const int vr = __shfl_sync(FULL, vrow_self, r);
-                    const unsigned long long dptr = __shfl_sync(FULL, reinterpret_cast<unsigned long long>(optr) + done, r);
-                    if (col * 16 < vr) {
-                        const uint8_t* sp = s_out + r * DG_OUT_B + col * 16;
-                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr) + col * 16;
-                        if (col * 16 + 16 <= vr && (dptr & 15) == 0) {
-                            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(sp);
-                        } else {   // window edge or unaligned first chunk: byte stores
-                            const int nbyte = min(16, vr - col * 16);
-                            for (int k = 0; k < nbyte; ++k) d[k] = sp[k];
-                        }
-                    }
-                }
-                __syncwarp();
-                if (rem > 0) { rem -= 128; done += 128; }
-            }
-            bitpos += consumed;
-            if (rem <= 0) rem = 0;
-        }
-    }
+// Status word of mua_decode (int32 [1], zeroed by the caller): 0 = ok; MUA_DEC_BAD_OFFSET = some chunk's side-info bit
+// offset lies past its slot (an encode that overflowed, or corrupt side info): the chunk is skipped, nothing outside the
+// stream buffer is read; MUA_DEC_BAD_TABLE = the table block does not match the S/K/Lmax the host passed, or a channel's
+// peak >= S / SCLV row >= K: nothing (or not that channel) is decoded.
+__device__ __forceinline__ void dec_flag(int32_t* status, int code) {
+    if (status) atomicMax(status, code);
 }
 
 // ---- general decoder with variable-count lookups (every codebook the lane / fast decoders do not take) ----
-// k_decode_gen decodes a FIXED number of symbols per lookup (1 for S >= 7: W = Lmax bits) from per-(peak,row) tables
-// that outgrow shared memory (S = 9: 212 KB, read through L1/L2): 17 instructions and one global load per symbol.
-// Here a lookup decodes AS MANY whole symbols as its Wv-bit window holds (at most 4; the SCLV codes of skewed MUA
+// (Its round-1 predecessor decoded a FIXED number of symbols per lookup -- 1 for S >= 7 -- from per-(peak,row) tables
+// that outgrow shared memory: 17 instructions and one global load per symbol; removed.)
+// A lookup decodes AS MANY whole symbols as its Wv-bit window holds (at most 4; the SCLV codes of skewed MUA
 // counts are 1..2 bits for the frequent symbols, so mostly 4) from rank tables per codebook ROW (K x 2^Wv entries,
 // <= 72 KB: always in shared memory); the lane's peak is applied by the PRMT that unpacks an entry (S <= 8: one PRMT
 // into the 8-byte rank -> symbol map; S >= 9: two PRMTs into the halves of the 16-byte map and a select).  Decoded
 // symbols are appended to a 64-bit register queue and leave for the output tile one 4-byte word at a time, so the
 // tile and the write-out are those of the fixed-count decoders.  Same chunk bookkeeping and stream staging (one TMA
-// bulk copy per lane and stage, sized for MUA_DV_PPS periods) as k_decode_gen.  One persistent CTA per SM with as many warps as fit beside
+// bulk copy per lane and stage, sized for MUA_DV_PPS periods).  One persistent CTA per SM with as many warps as fit beside
 // the tables.
 constexpr int DV_WARPS = 20;            // at most; the launch takes as many as fit beside the tables
 
@@ -196,7 +53,10 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
     extern __shared__ __align__(128) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, Wv = T->Wv;
-    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->decv_off == 0 || (WIDE != (T->S > 8))) return;
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->decv_off == 0 || (WIDE != (T->S > 8))) {
+        if (threadIdx.x == 0) dec_flag(P.status, MUA_DEC_BAD_TABLE);   // host view does not match the table block
+        return;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int STR_W = P.var_str_w;                                                   // staged stream words per lane
     const int per_warp = 32 * STR_W * 4 + 32 * DG_OUT_B + 16;
@@ -249,13 +109,21 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                 const int nch = (end + TILE - 1) / TILE - j0;
                 if (j < nch) {
                     const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
-                    rem = b - a;
-                    bitpos = P.chunk_off[(size_t)c * P.chunk_stride + j];
-                    sbase = P.stream + (size_t)c * P.slot_bytes;
-                    optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
-                    tab += (size_t)P.enc[c] << Wv;
-                    const uint4 mp = reinterpret_cast<const uint4*>(s_map)[P.peak[c]];
-                    m0 = mp.x; m1 = mp.y; m2 = mp.z; m3 = mp.w;
+                    const uint32_t bp0 = P.chunk_off[(size_t)c * P.chunk_stride + j];
+                    const int pk = P.peak[c], en = P.enc[c];
+                    if (pk >= T->S || en >= K) {
+                        dec_flag(P.status, MUA_DEC_BAD_TABLE);
+                    } else if (((bp0 >> 7) << 4) >= slot_bytes) {
+                        dec_flag(P.status, MUA_DEC_BAD_OFFSET);
+                    } else {
+                        rem = b - a;
+                        bitpos = bp0;
+                        sbase = P.stream + (size_t)c * P.slot_bytes;
+                        optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
+                        tab += (size_t)en << Wv;
+                        const uint4 mp = reinterpret_cast<const uint4*>(s_map)[pk];
+                        m0 = mp.x; m1 = mp.y; m2 = mp.z; m3 = mp.w;
+                    }
                 }
             }
         }
@@ -264,7 +132,12 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
         uint32_t fill8 = 0;                                      // 8 x their number (0, 8, 16, 24)
         while (__any_sync(FULL, rem > 0)) {
             // ---- stage 272 stream bytes per lane (one TMA bulk copy each), from the 16-byte unit holding `bitpos` ----
-            const uint32_t cur_al = (bitpos >> 7) << 4;
+            uint32_t cur_al = (bitpos >> 7) << 4;
+            if (rem > 0 && cur_al >= slot_bytes) {               // ran past the slot (corrupt stream): drop the rest of the chunk
+                dec_flag(P.status, MUA_DEC_BAD_OFFSET);
+                rem = 0;
+                cur_al = 0;
+            }
             const uint32_t nbytes = rem > 0 ? min((uint32_t)(STR_W * 4), slot_bytes - cur_al) : 0u;
             const uint32_t total = __reduce_add_sync(FULL, nbytes);
             __syncwarp();
@@ -369,7 +242,10 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
     extern __shared__ __align__(128) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K, W = T->W;
-    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->Lmax > 2) return;   // host view does not match the table block
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->Lmax > 2) {
+        if (threadIdx.x == 0) dec_flag(P.status, MUA_DEC_BAD_TABLE);   // host view does not match the table block
+        return;
+    }
     const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* s_str = dsm + warp * DF_PER_WARP;
@@ -410,11 +286,19 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
                 const int nch = (end + TILE - 1) / TILE - j0;
                 if (j < nch) {
                     const int a = max(start, (j0 + j) * TILE), b = min(end, (j0 + j + 1) * TILE);
-                    rem = b - a;
-                    bp = P.chunk_off[(size_t)c * P.chunk_stride + j];
-                    sbase = P.stream + (size_t)c * P.slot_bytes;
-                    optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
-                    lut += (size_t)((int)P.peak[c] * K + (int)P.enc[c]) << W;
+                    const uint32_t bp0 = P.chunk_off[(size_t)c * P.chunk_stride + j];
+                    const int pk = P.peak[c], en = P.enc[c];
+                    if (pk >= T->S || en >= K) {
+                        dec_flag(P.status, MUA_DEC_BAD_TABLE);
+                    } else if (((bp0 >> 7) << 4) >= slot_bytes) {
+                        dec_flag(P.status, MUA_DEC_BAD_OFFSET);
+                    } else {
+                        rem = b - a;
+                        bp = bp0;
+                        sbase = P.stream + (size_t)c * P.slot_bytes;
+                        optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
+                        lut += (size_t)(pk * K + en) << W;
+                    }
                 }
             }
         }
@@ -553,7 +437,7 @@ __device__ __forceinline__ DecRaw dec_load(const DecParams& P, long long item, l
     return r;
 }
 
-__device__ __forceinline__ DecItem dec_finish(const DecParams& P, DecRaw r, int K) {
+__device__ __forceinline__ DecItem dec_finish(const DecParams& P, DecRaw r, int K, int S) {
     // nothing derived from the loaded values may be scheduled before this point
     asm volatile("" : "+r"(r.start), "+r"(r.end), "+r"(r.pk), "+r"(r.en), "+r"(r.bp), "+l"(r.off));
     DecItem it;
@@ -561,7 +445,11 @@ __device__ __forceinline__ DecItem dec_finish(const DecParams& P, DecRaw r, int 
     if (r.valid && r.end > r.start && r.start >= 0) {
         const int j0 = r.start / TILE;
         const int nch = (r.end + TILE - 1) / TILE - j0;
-        if (r.j < nch) {
+        if (r.j < nch && (r.pk >= S || r.en >= K)) {
+            dec_flag(P.status, MUA_DEC_BAD_TABLE);
+        } else if (r.j < nch && (long long)(r.bp >> 3) >= P.slot_bytes) {
+            dec_flag(P.status, MUA_DEC_BAD_OFFSET);
+        } else if (r.j < nch) {
             const int a = max(r.start, (j0 + r.j) * TILE), b = min(r.end, (j0 + r.j + 1) * TILE);
             it.rem = b - a;
             it.bp = r.bp;
@@ -604,7 +492,10 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
     extern __shared__ __align__(128) uint8_t dsm[];
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K;
-    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->W != 8 || K > DL_MAX_ROWS || T->S > 8) return;
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->W != 8 || K > DL_MAX_ROWS || T->S > 8) {
+        if (threadIdx.x == 0) dec_flag(P.status, MUA_DEC_BAD_TABLE);   // host view does not match the table block
+        return;
+    }
     const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // ---- shared-memory layout: rank -> symbol maps, then per-(warp, chain) buffers below and above the tables,
@@ -681,7 +572,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
     DecRing R[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        cur[c] = dec_finish(P, dec_load(P, (g * NC + c) * 32 + lane, g < ngroups ? nitems : 0), K);
+        cur[c] = dec_finish(P, dec_load(P, (g * NC + c) * 32 + lane, g < ngroups ? nitems : 0), K, T->S);
         ring_start(cur[c], R[c], ring_a[c]);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -802,7 +693,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
                 const long long nlim = gn < ngroups ? nitems : 0;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    cur[c] = dec_finish(P, dec_load(P, (gn * NC + c) * 32 + lane, nlim), K);
+                    cur[c] = dec_finish(P, dec_load(P, (gn * NC + c) * 32 + lane, nlim), K, T->S);
                     ring_start(cur[c], R[c], ring_a[c]);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");

@@ -31,7 +31,23 @@ struct EncParams {
     int32_t chunk_stride;
     int64_t* total_bits;
     int32_t* overflow;
+    // multi-GPU report sink (mua_report_sink): row (row0 + c) of every peer's int32 [C_total][4] report buffer
+    int32_t n_peers;
+    int64_t row0;
+    int32_t* rep[MUA_MAX_PEERS];
 };
+
+// Channel epilogue of every encoder: the bit count for the local caller and -- when a report sink is attached -- the channel's
+// report row {bits, window symbols, SCLV row, peak} (get_BR_no_sort.py:282-287: what the BR report needs) stored straight
+// into every peer's report buffer, one 16-byte store per peer over NVLink (lane p serves peer p): the "gather" of the
+// multi-GPU step costs no kernel and no collective.
+__device__ __forceinline__ void publish_channel(const EncParams& P, int c, uint32_t Pbits, int start, int end, int pk, int en, int lane) {
+    if (lane == 0) P.total_bits[c] = Pbits;
+    if (lane < P.n_peers) {
+        const int4 row = make_int4((int)Pbits, max(end - start, 0), en, pk);
+        *reinterpret_cast<int4*>(P.rep[lane] + 4 * (P.row0 + c)) = row;
+    }
+}
 
 constexpr int ENC_WARPS = 8;
 constexpr int ENC_NST = 4;   // TMA stages per warp
@@ -66,7 +82,7 @@ __device__ __forceinline__ void flush_units(const uint32_t* s_ring, uint8_t* out
             v4.x = bswap32(v4.x); v4.y = bswap32(v4.y); v4.z = bswap32(v4.z); v4.w = bswap32(v4.w);
             *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
         } else {
-            *overflow = 1;
+            *overflow = MUA_ENC_OVERFLOW;
         }
     }
 }
@@ -87,7 +103,7 @@ __device__ __forceinline__ void flush_last(const uint32_t* s_ring, uint8_t* out,
         v4.w = __shfl_sync(FULL, val, 3);
         if (lane == 0) {
             if (u < slot_units) *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
-            else *overflow = 1;
+            else *overflow = MUA_ENC_OVERFLOW;
         }
     }
 }
@@ -294,7 +310,7 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
     const int K = T->K;
     constexpr int S = SV;
     if (T->S != SV || S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || S > 4 || T->enc4_off == 0 || (lut4_saddr & 255u)) {
-        if (threadIdx.x == 0) *P.overflow = 2;   // launch configuration does not match the table block
+        if (threadIdx.x == 0) *P.overflow = MUA_ENC_BAD_TABLE;   // launch configuration does not match the table block
         return;
     }
     if (lane == 0) {
@@ -319,8 +335,11 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
         const int start = P.start[c];
         const int end = min(P.end[c], n);
         uint32_t Pbits = 0;
-        if (end > start && start >= 0) {
-            const int combo = (int)P.peak[c] * K + (int)P.enc[c];
+        const int pk_c = P.peak[c], en_c = P.enc[c];
+        if (pk_c >= P.S || en_c >= K) {                   // not a channel state this table block can code: flag, encode nothing
+            if (lane == 0) *P.overflow = MUA_ENC_BAD_TABLE;
+        } else if (end > start && start >= 0) {
+            const int combo = pk_c * K + en_c;
             if (combo != cur_combo) {   // this (peak, codebook row) pair's LUTs: 512 B + 64 B
                 __syncwarp();
                 reinterpret_cast<uint4*>(sm + SM::LUT4)[lane] = g_enc4[(size_t)combo * 32 + lane];
@@ -381,7 +400,7 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
             flush_last<RM>(s_ring, out, Pbits, carry, slot_units, P.overflow, lane);
             __syncwarp();
         }
-        if (lane == 0) P.total_bits[c] = Pbits;
+        publish_channel(P, c, Pbits, start, end, pk_c, en_c, lane);
     }
 }
 
@@ -413,7 +432,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K;
     if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || TILE * T->Lmax > (SM::RW - 8) * 32) {
-        if (threadIdx.x == 0) *P.overflow = 2;
+        if (threadIdx.x == 0) *P.overflow = MUA_ENC_BAD_TABLE;
         return;
     }
     if (lane == 0) {
@@ -435,8 +454,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
         const int start = P.start[c];
         const int end = min(P.end[c], n);
         uint32_t Pbits = 0;
-        if (end > start && start >= 0) {
-            const int combo = (int)P.peak[c] * K + (int)P.enc[c];
+        const int pk_c = P.peak[c], en_c = P.enc[c];
+        if (pk_c >= P.S || en_c >= K) {                   // not a channel state this table block can code: flag, encode nothing
+            if (lane == 0) *P.overflow = MUA_ENC_BAD_TABLE;
+        } else if (end > start && start >= 0) {
+            const int combo = pk_c * K + en_c;
             if (combo != cur_combo) {
                 __syncwarp();
                 const uint4* src = g_enc2 + (size_t)combo * 64;
@@ -557,7 +579,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
             flush_last<RM>(s_ring, out, Pbits, carry, slot_units, P.overflow, lane);
             __syncwarp();
         }
-        if (lane == 0) P.total_bits[c] = Pbits;
+        publish_channel(P, c, Pbits, start, end, pk_c, en_c, lane);
     }
 }
 
@@ -607,7 +629,7 @@ __device__ __forceinline__ void flush_units_z(uint32_t* s_ring, uint8_t* out, ui
             v4.x = bswap32(v4.x); v4.y = bswap32(v4.y); v4.z = bswap32(v4.z); v4.w = bswap32(v4.w);
             *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
         } else {
-            *overflow = 1;
+            *overflow = MUA_ENC_OVERFLOW;
         }
     }
 }
@@ -710,7 +732,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K;
     if (T->S != SV || SV != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 8 || T->encp_off == 0 || (lutp_saddr & 255u)) {
-        if (threadIdx.x == 0) *P.overflow = 2;   // launch configuration does not match the table block
+        if (threadIdx.x == 0) *P.overflow = MUA_ENC_BAD_TABLE;   // launch configuration does not match the table block
         return;
     }
     if (lane == 0) {
@@ -732,8 +754,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
         const int start = P.start[c];
         const int end = min(P.end[c], n);
         uint32_t Pbits = 0;
-        if (end > start && start >= 0) {
-            const int combo = (int)P.peak[c] * K + (int)P.enc[c];
+        const int pk_c = P.peak[c], en_c = P.enc[c];
+        if (pk_c >= P.S || en_c >= K) {                   // not a channel state this table block can code: flag, encode nothing
+            if (lane == 0) *P.overflow = MUA_ENC_BAD_TABLE;
+        } else if (end > start && start >= 0) {
+            const int combo = pk_c * K + en_c;
             if (combo != cur_combo) {   // this (peak, codebook row) pair's table: 512 B
                 __syncwarp();
                 reinterpret_cast<uint4*>(sm + SM::LUTP)[lane] = g_encp[(size_t)combo * 32 + lane];
@@ -796,12 +821,111 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
                     v4.x = bswap32(v4.x); v4.y = bswap32(v4.y); v4.z = bswap32(v4.z); v4.w = bswap32(v4.w);
                     *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
                 } else {
-                    *P.overflow = 1;
+                    *P.overflow = MUA_ENC_OVERFLOW;
                 }
             }
             __syncwarp();
         }
-        if (lane == 0) P.total_bits[c] = Pbits;
+        publish_channel(P, c, Pbits, start, end, pk_c, en_c, lane);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// report sink flags (mua_report_signal / mua_report_wait)
+// ---------------------------------------------------------------------------------------------
+struct PeerFlags {
+    int32_t n, rank;
+    int32_t* flags[MUA_MAX_PEERS];   // int32 [MUA_MAX_PEERS + 1] on every peer
+};
+
+// Enqueued after the encoder on the same stream: the encoder's peer stores are complete (kernel boundary); the fence +
+// system-scope release store publish them to the peer that polls the flag.
+__global__ void k_report_signal(const __grid_constant__ PeerFlags F, int32_t step) {
+    const int p = threadIdx.x;
+    if (p < F.n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(F.flags[p] + F.rank), "r"(step) : "memory");
+    }
+}
+
+// lane p polls the flag of source rank p in the OWN flag block; gives up after `max_cycles` (sticky marker in slot MUA_MAX_PEERS)
+__global__ void k_report_wait(const __grid_constant__ PeerFlags F, int32_t step, long long max_cycles) {
+    const int p = threadIdx.x;
+    if (p < F.n) {
+        const int32_t* f = F.flags[F.rank] + p;
+        const long long t0 = clock64();
+        int32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v >= step) break;
+            if (clock64() - t0 > max_cycles) {
+                F.flags[F.rank][MUA_MAX_PEERS] = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// dense packing of the per-channel slots (mua_pack_streams): what a caller ships off the device
+// ---------------------------------------------------------------------------------------------
+// unit_off[c] = sum_{i<c} ceil(total_bits[i] / 128) (16-byte units), unit_off[C] = total: one CTA, chunked block scan.
+__global__ void __launch_bounds__(1024) k_pack_offsets(const int64_t* __restrict__ total_bits, int C, int64_t slot_units,
+                                                       int64_t* __restrict__ unit_off) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < C; c0 += 1024) {
+        const int c = c0 + threadIdx.x;
+        long long u = 0;
+        if (c < C) {
+            u = (total_bits[c] + 127) >> 7;
+            if (u > slot_units) u = slot_units;              // an overflowed slot holds no more than this
+        }
+        long long incl = u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long t = __shfl_up_sync(FULL, wi, d);
+                if (lane >= d) wi += t;
+            }
+            s_warp[lane] = wi - w;                           // exclusive
+        }
+        __syncthreads();
+        const long long base = s_base;
+        if (c < C) unit_off[c] = base + s_warp[warp] + incl - u;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base = base + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) unit_off[C] = s_base;
+}
+
+// warp per channel: copy the used 16-byte units of the slot to the dense buffer (coalesced both ways)
+__global__ void __launch_bounds__(256) k_pack_copy(const uint8_t* __restrict__ stream, int64_t slot_bytes, int C,
+                                                   const int64_t* __restrict__ unit_off, uint8_t* __restrict__ dense,
+                                                   int64_t dense_units) {
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < C; c += nw) {
+        const long long o = unit_off[c], n = unit_off[c + 1] - o;
+        const uint4* src = reinterpret_cast<const uint4*>(stream + (size_t)c * slot_bytes);
+        uint4* dst = reinterpret_cast<uint4*>(dense) + o;
+        for (long long i = lane; i < n; i += 32)
+            if (o + i < dense_units) dst[i] = src[i];
     }
 }
 

@@ -88,3 +88,97 @@ def br_report(report, BP):
         return {"avg_bits_per_symbol": avg, "BR": np.mean(avg) / (BP / 1000),
                 "total_bits": int(r[:, 0].sum()), "total_symbols": int(r[:, 1].sum()),
                 "enc": r[:, 2].astype(np.uint8), "peak": r[:, 3].astype(np.uint8)}
+
+
+class _DevMem:
+    """raw device allocation -> torch tensor (zero-copy) through __cuda_array_interface__"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerReport:
+    """The multi-GPU report WITHOUT a collective (include/mua_b200.h "multi-GPU report sink"): every rank owns two report
+    buffers int32 [C_total, 4] (alternated by step parity) and a flag block in one cudaMalloc'd, IPC-exported allocation;
+    all ranks map each other's allocation (cudaIpcOpenMemHandle, NVLink peer access).  The encoder (pipeline.encode(sink=...))
+    stores each channel's row {bits, symbols, SCLV row, peak} into all ranks' buffers in its channel epilogue;
+    `signal(step)` after the encoder publishes "my rows are written", `wait(step)` -- enqueued where the report is needed,
+    e.g. after the round-trip decode -- returns on the stream once every rank's rows of that step have landed.
+
+    One process per GPU of one node; the handles travel through torch.distributed (all_gather_object)."""
+
+    def __init__(self, C_local, C_total, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib.load(), C
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        assert self.world <= _lib.MAX_PEERS
+        lo, hi = shard_range(C_total, self.rank, self.world)
+        assert hi - lo == C_local, "local shard does not match shard_range()"
+        self.C_total, self.row0 = int(C_total), int(lo)
+        self.rep_bytes = (C_total * 16 + 255) // 256 * 256
+        self.nbytes = 2 * self.rep_bytes + 256
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        own = C.c_void_p()
+        handle = (C.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+        _lib.check(self._lib.mua_peer_alloc(self.nbytes, C.byref(own), handle))
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.base = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.base.append(self.own)
+                continue
+            p = C.c_void_p()
+            hb = (C.c_uint8 * _lib.IPC_HANDLE_BYTES).from_buffer_copy(handles[r])
+            _lib.check(self._lib.mua_peer_open(hb, C.byref(p)))
+            self.base.append(p.value)
+        self._mem = _DevMem(self.own, self.nbytes)
+        self._own_t = torch.as_tensor(self._mem, device=self.dev)
+        self._sinks = []
+        for parity in range(2):
+            s = _lib.ReportSink()
+            s.n_peers, s.rank, s.row0 = self.world, self.rank, self.row0
+            for r in range(self.world):
+                s.d_report[r] = self.base[r] + parity * self.rep_bytes
+                s.d_flags[r] = self.base[r] + 2 * self.rep_bytes
+            self._sinks.append(s)
+        dist.barrier(group=group)                       # every rank has mapped every buffer before anyone stores into them
+
+    def sink(self, step):
+        """the sink of step `step` (1, 2, ...): pass to pipeline.encode"""
+        return self._sinks[step & 1]
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def signal(self, step):
+        from . import _lib
+        _lib.check(self._lib.mua_report_signal(self._C.byref(self._sinks[step & 1]), int(step), self._stream()))
+
+    def wait(self, step):
+        from . import _lib
+        _lib.check(self._lib.mua_report_wait(self._C.byref(self._sinks[step & 1]), int(step), self._stream()))
+
+    def report(self, step):
+        """int32 [C_total, 4] view of the own buffer of that step's parity (valid after wait(step) has completed)"""
+        off = (step & 1) * self.rep_bytes
+        return self._own_t[off: off + self.C_total * 16].view(torch.int32).view(self.C_total, 4)
+
+    def timed_out(self):
+        flags = self._own_t[2 * self.rep_bytes:].view(torch.int32)
+        return bool(flags[16].item())
+
+    def close(self):
+        from . import _lib
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+        for r, p in enumerate(self.base):
+            if r != self.rank and p:
+                self._lib.mua_peer_close(self._C.c_void_p(p))
+        self._own_t = None
+        self._lib.mua_peer_free(self._C.c_void_p(self.own))
+        self.base = []

@@ -246,8 +246,9 @@ class EncodedStreams:
         return self.stream[c, :nb].cpu().numpy()
 
 
-def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None, out: EncodedStreams = None):
-    """Stage 5 (mua_encode): window [start[c], end[c]) of every channel -> per-channel bitstreams."""
+def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None, out: EncodedStreams = None, sink=None):
+    """Stage 5 (mua_encode): window [start[c], end[c]) of every channel -> per-channel bitstreams.
+    sink: a `_lib.ReportSink` (dist.PeerReport.sink(step)): every channel's report row is also stored into all peers' buffers."""
     lib = _lib.load()
     dev = rec.device
     start = start.to(torch.int32).contiguous()
@@ -268,16 +269,46 @@ def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None,
         _lib.check(lib.mua_encode(*rec.layout_args(), cb.S, _ptr(start), _ptr(end), _ptr(peak), _ptr(enc),
                                   _ptr(cb.d_tables), cb.K, cb.Lmax, _ptr(out.stream), out.slot_bytes,
                                   _ptr(out.chunk_off), out.chunk_stride, _ptr(out.total_bits), _ptr(out.overflow),
-                                  _stream()))
+                                  C.byref(sink) if sink is not None else None, _stream()))
     return out
 
 
+def pack_streams(es: EncodedStreams, dense: torch.Tensor = None, unit_off: torch.Tensor = None):
+    """mua_pack_streams: the used 16-byte units of every slot back to back.  Returns (dense uint8 buffer, unit_off int64
+    [C + 1]); stream of channel c = dense[16 * unit_off[c] : 16 * unit_off[c + 1]], total bytes = 16 * unit_off[C]."""
+    lib = _lib.load()
+    Cn = es.stream.shape[0]
+    if dense is None:
+        dense = torch.empty(Cn * es.slot_bytes, dtype=torch.uint8, device=es.stream.device)
+    if unit_off is None:
+        unit_off = torch.empty(Cn + 1, dtype=torch.int64, device=es.stream.device)
+    with torch.cuda.device(es.stream.device):
+        _lib.check(lib.mua_pack_streams(_ptr(es.stream), es.slot_bytes, _ptr(es.total_bits), Cn, _ptr(unit_off), _ptr(dense),
+                                        dense.numel(), _stream()))
+    return dense, unit_off
+
+
+_DEC_STATUS = {_lib.DEC_BAD_OFFSET: "a chunk's bit offset lies past its slot (encode overflowed its slots, or corrupt side info)",
+               _lib.DEC_BAD_TABLE: "the table block does not match the codebook's S/K/Lmax, or a channel's peak/SCLV row is out of range"}
+
+
 def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, enc, out: torch.Tensor = None,
-           max_end: int = 0):
+           max_end: int = 0, status: torch.Tensor = None):
     """Stage 6 (mua_decode): symbols written back at their absolute bin index into a buffer with the
     layout of `rec.sym` (bytes outside the window are left as they were; a fresh buffer is zeroed).
-    max_end: host-known upper bound of `end` (0 = unknown); it only trims the launch."""
+    max_end: host-known upper bound of `end` (0 = unknown); it only trims the launch.
+    status : int32 [1] device tensor that receives the decoder's status word (include/mua_b200.h MUA_DEC_*).  Without it
+             the call is CHECKED: it refuses streams whose encode flagged an overflow / table mismatch and raises if the
+             decoder reports one (one device synchronisation).  Pass a tensor to stay asynchronous (the caller zeroes and
+             reads it; `check_decode_status`)."""
     lib = _lib.load()
+    checked = status is None
+    if checked:
+        ov = int(es.overflow.item())
+        if ov:
+            raise _lib.MuaError("decode refused: the encoder flagged %s" % ("a stream that did not fit its slot" if ov == _lib.ENC_OVERFLOW
+                                                                           else "a table / channel-state mismatch"))
+        status = torch.zeros(1, dtype=torch.int32, device=rec.device)
     if out is None:
         out = torch.zeros_like(rec.sym)
     start = start.to(torch.int32).contiguous()
@@ -287,8 +318,17 @@ def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, e
     with torch.cuda.device(rec.device):
         _lib.check(lib.mua_decode(_ptr(es.stream), es.slot_bytes, _ptr(es.chunk_off), es.chunk_stride, _ptr(rec.off),
                                   int(rec.stride), rec.C, cb.S, _ptr(start), _ptr(end), _ptr(peak), _ptr(enc),
-                                  _ptr(cb.d_tables), cb.K, cb.Lmax, int(max_end), _ptr(out), _stream()))
+                                  _ptr(cb.d_tables), cb.K, cb.Lmax, int(max_end), _ptr(out), _ptr(status), _stream()))
+    if checked:
+        check_decode_status(status)
     return out
+
+
+def check_decode_status(status: torch.Tensor):
+    """raise if a decode reported MUA_DEC_* in `status` (synchronises)."""
+    st = int(status.item())
+    if st:
+        raise _lib.MuaError("mua_decode status %d: %s" % (st, _DEC_STATUS.get(st, "unknown")))
 
 
 def verify(rec: Recording, dec: torch.Tensor, S: int, start, end):

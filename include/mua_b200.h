@@ -11,7 +11,9 @@
  *   - plain pointers and sizes only; every `d_*` pointer is DEVICE memory owned by the caller, every
  *     `h_*` pointer is HOST memory.  No hidden allocation, no retained state between calls.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
- *     enqueued asynchronously on it; nothing synchronises the device.
+ *     enqueued asynchronously on it; no per-step call synchronises the device.  The one exception is the
+ *     one-off setup call mua_build_tables, which waits for `stream` before it returns (its table header is
+ *     uploaded from the caller's stack frame).
  *   - return value: 0 = ok, <0 = error (MUA_E_*); mua_last_error() returns a thread-local message.
  *   - re-entrant across distinct streams/devices.
  *
@@ -37,15 +39,26 @@
 extern "C" {
 #endif
 
-#define MUA_ABI_VERSION 1
+#define MUA_ABI_VERSION 2
 #define MUA_CHUNK 1024        /* symbols per decode chunk */
 #define MUA_MAX_S 10          /* symbols per alphabet: 2..10 (get_BR_no_sort.py:104) */
 #define MUA_MAX_K 35          /* candidate SCLVs for S=10 (Stored_SCLVs_S_10.pkl) */
 #define MUA_MAX_H 16          /* history lengths per calibrate call (scripts use 9: 2^2..2^10) */
+#define MUA_MAX_PEERS 16      /* GPUs of one node that can share a report sink */
+#define MUA_IPC_HANDLE_BYTES 64
 
 #define MUA_OK 0
 #define MUA_E_INVALID (-1)    /* bad argument (message says which) */
 #define MUA_E_CUDA (-2)       /* CUDA runtime error (message holds cudaGetErrorString) */
+
+/* device-side flags: *d_overflow of mua_encode, *d_status of mua_decode (int32, zeroed by the caller, 0 = ok) */
+#define MUA_ENC_OVERFLOW 1    /* a stream did not fit its slot (nothing was written past the slot) */
+#define MUA_ENC_BAD_TABLE 2   /* table block does not match S/K/Lmax, or a channel's peak >= S / SCLV row >= K
+                                 (that channel is not encoded: total_bits 0) */
+#define MUA_DEC_BAD_OFFSET 1  /* a chunk's side-info bit offset lies past its slot (overflowed encode, corrupt side
+                                 info): the chunk is skipped, nothing outside the stream buffer is read */
+#define MUA_DEC_BAD_TABLE 2   /* table block does not match S/K/Lmax (nothing is decoded), or a channel's peak >= S /
+                                 SCLV row >= K (that channel is skipped) */
 
 /* window rule for the post-calibration ("to be compressed") window */
 #define MUA_WINDOW_NONE 0     /* calibration only: no post window is scanned */
@@ -166,6 +179,38 @@ int mua_bit_counts(const int32_t* d_hist, const uint8_t* d_enc, int64_t N, const
 int mua_elim_scores(const uint8_t* d_enc, const int64_t* d_min1, const int64_t* d_min2, int64_t N,
                     int32_t K, int64_t* d_assign_hist, int64_t* d_score, void* stream);
 
+/* ---- multi-GPU report sink ("only the per-channel bit counts and chosen-SCLV indices are gathered") ---------
+ *
+ * Channels shard over the GPUs of a node; what the BR report needs from every channel is 16 bytes: {bit count, window
+ * symbols, SCLV row, peak} (get_BR_no_sort.py:282-291).  Instead of gathering them with a collective after the local
+ * kernels, the encoder stores each channel's row straight into EVERY peer's report buffer through NVLink peer memory (one
+ * 16-byte store per peer in the channel epilogue), so the transfer rides on the encode; a flag per source rank tells a
+ * consumer when a step's rows have landed.
+ *
+ *   mua_peer_alloc   cudaMalloc + zero + cudaIpcGetMemHandle: the ONE allocating entry point of the library (IPC handles
+ *                    need a whole allocation).  h_handle receives MUA_IPC_HANDLE_BYTES to hand to the other processes.
+ *   mua_peer_open    map another process's buffer (cudaIpcOpenMemHandle, peer access enabled lazily); mua_peer_close unmaps.
+ *   mua_peer_free    cudaFree of an own buffer.
+ *   mua_report_signal  enqueue after mua_encode: rank `sink->rank` tells every peer "my rows of step `step` are written"
+ *                    (system-scope release store of `step` into d_flags[peer][rank]).
+ *   mua_report_wait  enqueue where the report is needed: returns (on the stream) once d_flags[rank][p] >= step for every peer
+ *                    p; gives up after ~2 s and stores 1 into d_flags[rank][MUA_MAX_PEERS] instead of hanging the device.
+ * Steps are numbered 1, 2, ...; callers alternate two report buffers by step parity, so a peer that is one step ahead
+ * never overwrites rows that are still being read (a rank cannot be two steps ahead: its wait needs every peer's signal). */
+typedef struct mua_report_sink {
+    int32_t n_peers;                       /* ranks sharing the report (<= MUA_MAX_PEERS); 0 = no sink */
+    int32_t rank;                          /* this process's index */
+    int64_t row0;                          /* global index of this rank's first channel */
+    int32_t* d_report[MUA_MAX_PEERS];      /* int32 [C_total][4] on every peer (entry `rank` = the own buffer) */
+    int32_t* d_flags[MUA_MAX_PEERS];       /* int32 [MUA_MAX_PEERS + 1] on every peer: [p] = last step signalled by rank p */
+} mua_report_sink;
+int mua_peer_alloc(size_t bytes, void** d_ptr, uint8_t* h_handle);
+int mua_peer_open(const uint8_t* h_handle, void** d_ptr);
+int mua_peer_close(void* d_ptr);
+int mua_peer_free(void* d_ptr);
+int mua_report_signal(const mua_report_sink* h_sink, int32_t step, void* stream);
+int mua_report_wait(const mua_report_sink* h_sink, int32_t step, void* stream);
+
 /* ---- stage 5: Huffman encode -------------------------------------------------------------- */
 
 /* Encode window [d_start[c], d_end[c]) (d_end <= len; d_end <= d_start encodes nothing) of every
@@ -173,27 +218,41 @@ int mua_elim_scores(const uint8_t* d_enc, const int64_t* d_min1, const int64_t* 
  *   d_stream      : C slots of `slot_bytes` (multiple of 16); slot c holds the padded stream
  *   d_chunk_off   : uint32 [C][chunk_stride]; entry j = bit offset of chunk j (see header comment)
  *   d_total_bits  : int64 [C]  (== SCLV[enc] . mapped post histogram, get_BR_no_sort.py:287)
- *   d_overflow    : int32 [1], set to 1 when a stream did not fit its slot, 2 when K/Lmax do not
- *                   match the table block (caller zeroes it)
+ *   d_overflow    : int32 [1], MUA_ENC_OVERFLOW when a stream did not fit its slot, MUA_ENC_BAD_TABLE when
+ *                   S/K/Lmax do not match the table block or a channel's peak/row is out of range
+ *                   (caller zeroes it)
  *   K, Lmax       : rows and longest codeword of the table block (as passed to mua_build_tables);
- *                   host-side launch configuration only, the kernels cross-check them */
+ *                   host-side launch configuration only, the kernels cross-check them
+ *   h_sink        : NULL, or the multi-GPU report sink: row (row0 + c) = {total_bits, max(end - start, 0), enc, peak}
+ *                   as int32 is also stored into every peer's d_report (bit counts must fit int32: T * Lmax < 2^31) */
 int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
                int32_t T, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end,
                const uint8_t* d_peak, const uint8_t* d_enc, const void* d_tables, int32_t K,
                int32_t Lmax, uint8_t* d_stream, int64_t slot_bytes, uint32_t* d_chunk_off,
-               int32_t chunk_stride, int64_t* d_total_bits, int32_t* d_overflow, void* stream);
+               int32_t chunk_stride, int64_t* d_total_bits, int32_t* d_overflow,
+               const mua_report_sink* h_sink, void* stream);
+
+/* Pack the used part of every channel's slot back to back (what a caller ships off the device or stores: slots are sized for
+ * the worst case, a stream uses ceil(total_bits / 128) 16-byte units of its slot).
+ *   d_unit_off : int64 [C + 1] out: 16-byte unit offset of channel c in d_dense; [C] = total units
+ *   d_dense    : dense_bytes bytes (units past the end are dropped; size it C * slot_bytes to be safe) */
+int mua_pack_streams(const uint8_t* d_stream, int64_t slot_bytes, const int64_t* d_total_bits, int32_t C,
+                     int64_t* d_unit_off, uint8_t* d_dense, int64_t dense_bytes, void* stream);
 
 /* ---- stage 6: table-driven chunk-parallel decode ------------------------------------------ */
 
 /* Inverse of mua_encode: symbols are written back at their absolute bin index, i.e. d_dec uses the
  * same layout (d_off/stride) as the input; bytes outside [start,end) are not touched.
  * max_end: an upper bound of every d_end[c] known to the host (e.g. H + T/2), or 0 if unknown; it
- * only sizes the launch (chunks past it are never scheduled). */
+ * only sizes the launch (chunks past it are never scheduled).
+ * d_status: int32 [1], zeroed by the caller; MUA_DEC_BAD_OFFSET / MUA_DEC_BAD_TABLE (the larger one wins) when
+ * something was not decoded -- a decode after an encode that set MUA_ENC_OVERFLOW reports MUA_DEC_BAD_OFFSET
+ * for the chunks that start past the slot and garbage-free output cannot be assumed for the truncated channel. */
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off,
                int32_t chunk_stride, const int64_t* d_off, int64_t stride, int32_t C, int32_t S,
                const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
                const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end,
-               uint8_t* d_dec, void* stream);
+               uint8_t* d_dec, int32_t* d_status, void* stream);
 
 /* Round-trip check on the device: counts positions in [start,end) where d_dec != min(d_sym, S-1).
  * d_mismatch : uint64 [1] (zeroed by the call). */

@@ -55,26 +55,26 @@ int main(void) {
     CU(cudaMalloc(&d_tab, mua_tables_bytes(S, K)));
     CU(cudaMalloc((void**)&d_cut, C * sizeof(int32_t)));
     CU(cudaMalloc((void**)&d_end, C * sizeof(int32_t)));
-    CU(cudaMalloc((void**)&d_ovf, sizeof(int32_t)));
+    CU(cudaMalloc((void**)&d_ovf, 2 * sizeof(int32_t)));   /* [0] encode overflow flag, [1] decode status */
     CU(cudaMalloc((void**)&d_co, (size_t)C * chunk_stride * sizeof(uint32_t)));
     CU(cudaMalloc((void**)&d_bits, C * sizeof(int64_t)));
     CU(cudaMalloc((void**)&d_mis, sizeof(unsigned long long)));
     CU(cudaMemcpy(d_sym, h_sym, (size_t)C * stride, cudaMemcpyHostToDevice));
     CU(cudaMemset(d_dec, 0xEE, (size_t)C * stride));
-    CU(cudaMemset(d_ovf, 0, sizeof(int32_t)));
+    CU(cudaMemset(d_ovf, 0, 2 * sizeof(int32_t)));
 
     const int32_t hH[1] = {H};
     CK(mua_build_tables(d_tab, lens, codes, S, K, NULL));
     CK(mua_calibrate(d_sym, NULL, NULL, stride, T, C, S, hH, 1, 1, MUA_WINDOW_TRUNCATE, d_tab, 1u, 0u,
                      d_cut, d_end, d_peak, d_enc, NULL, NULL, NULL, NULL, NULL));
     CK(mua_encode(d_sym, NULL, NULL, stride, T, C, S, d_cut, d_end, d_peak, d_enc, d_tab, K, 2, d_stream, slot, d_co,
-                  chunk_stride, d_bits, d_ovf, NULL));
+                  chunk_stride, d_bits, d_ovf, NULL, NULL));
     CK(mua_decode(d_stream, slot, d_co, chunk_stride, NULL, stride, C, S, d_cut, d_end, d_peak, d_enc, d_tab, K, 2,
-                  H + T / 2, d_dec, NULL));
+                  H + T / 2, d_dec, d_ovf + 1, NULL));
     CK(mua_verify(d_sym, d_dec, NULL, stride, C, S, d_cut, d_end, d_mis, NULL));
     CU(cudaDeviceSynchronize());
 
-    int32_t h_cut[C], h_end[C], ovf;
+    int32_t h_cut[C], h_end[C], ovf[2];
     uint8_t h_peak[C];
     int64_t h_bits[C];
     unsigned long long mis;
@@ -82,9 +82,9 @@ int main(void) {
     CU(cudaMemcpy(h_end, d_end, sizeof h_end, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(h_peak, d_peak, sizeof h_peak, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(h_bits, d_bits, sizeof h_bits, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&ovf, d_ovf, sizeof ovf, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ovf, d_ovf, sizeof ovf, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&mis, d_mis, sizeof mis, cudaMemcpyDeviceToHost));
-    if (ovf || mis) { fprintf(stderr, "overflow %d, mismatches %llu\n", ovf, mis); return 1; }
+    if (ovf[0] || ovf[1] || mis) { fprintf(stderr, "encode flag %d, decode status %d, mismatches %llu\n", ovf[0], ovf[1], mis); return 1; }
 
     long long total = 0;
     for (int c = 0; c < C; ++c) {

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mua_abi_version() == 1
+    assert lib.mua_abi_version() == 2
     assert lib.mua_tables_bytes(3, 1) > 0 and lib.mua_tables_bytes(11, 1) == 0
 
 
