@@ -630,7 +630,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
         }
     } else {
         // variable-count lookups from per-row rank tables in shared memory: one persistent CTA per SM
-        const int fixed = 4 * MUA_MAX_S * 4 + 16 + (h.K << h.Wv) * 4;      // rank maps, ticket, tables
+        const int fixed = 4 * MUA_MAX_S * 4 + 16 + DV_LENS_B + (h.K << h.Wv) * 4;      // rank maps, ticket, SCLV rows, tables
         P.var_pps = MUA_DV_PPS;
         P.var_str_w = ((127 + 64 + P.var_pps * 131 * h.Lmax + 31) / 32 + 3) / 4 * 4;     // whole 16-byte units
         const int DV_PER_WARP = 32 * P.var_str_w * 4 + 32 * DG_OUT_B + 16;

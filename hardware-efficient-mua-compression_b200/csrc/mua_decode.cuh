@@ -46,7 +46,27 @@ __device__ __forceinline__ void dec_flag(int32_t* status, int code) {
 // tile and the write-out are those of the fixed-count decoders.  Same chunk bookkeeping and stream staging (one TMA
 // bulk copy per lane and stage, sized for MUA_DV_PPS periods).  One persistent CTA per SM with as many warps as fit beside
 // the tables.
+// entry (or a bare rank in the low nibble with the other slots set to "none") -> symbols, one per byte: the selectors index the
+// lane's rank -> symbol map (TabHdr::idx[peak]); S <= 8: one PRMT into the 8-byte map (selector 0x8 = sign replicate of byte 0 = a
+// zero byte); S >= 9: two PRMTs into the halves of the 16-byte map and a select by the selectors' bit 3 (0xF = entry 15 = zero)
+template <bool WIDE>
+__device__ __forceinline__ uint32_t dv_syms(uint32_t e, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    uint32_t syms;
+    if (!WIDE) {
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(syms) : "r"(m0), "r"(m1), "r"(e));
+    } else {
+        uint32_t slo, shi, msk;
+        const uint32_t e7 = e & 0x7777u;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(slo) : "r"(m0), "r"(m1), "r"(e7));
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(shi) : "r"(m2), "r"(m3), "r"(e7));
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(msk) : "r"(0x0000FF00u), "r"(0u), "r"((e >> 3) & 0x1111u));
+        syms = (slo & ~msk) | (shi & msk);
+    }
+    return syms;
+}
+
 constexpr int DV_WARPS = 20;            // at most; the launch takes as many as fit beside the tables
+constexpr int DV_LENS_B = (MUA_MAX_K * 16 + 127) / 128 * 128;
 
 template <bool WIDE>
 __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_constant__ DecParams P) {
@@ -65,7 +85,8 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + 32 * DG_OUT_B);
     uint32_t* s_map = reinterpret_cast<uint32_t*>(dsm + nwarps * per_warp);          // uint4 [MUA_MAX_S]: idx[p][0..15]
     uint32_t* s_ticket = s_map + 4 * MUA_MAX_S;                                      // next group of this CTA (4 words reserved)
-    uint32_t* s_tab = s_ticket + 4;
+    uint8_t* s_lens = reinterpret_cast<uint8_t*>(s_ticket + 4);                      // SCLV rows: uint8 [MUA_MAX_K][16]
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_lens + DV_LENS_B);
     if (lane == 0) {
         mbar_init(s_bar, 1);
         fence_barrier_init();
@@ -76,6 +97,7 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
         for (int i = threadIdx.x; i < (K << Wv); i += blockDim.x) s_tab[i] = g[i];
         const uint32_t* gi = reinterpret_cast<const uint32_t*>(&T->idx[0][0]);
         for (int i = threadIdx.x; i < 4 * MUA_MAX_S; i += blockDim.x) s_map[i] = gi[i];
+        for (int i = threadIdx.x; i < K * 16; i += blockDim.x) s_lens[i] = T->lens[i >> 4][i & 15];
     }
     __syncthreads();
     uint32_t parity = 0;
@@ -100,6 +122,7 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
         const uint8_t* sbase = P.stream;
         uint8_t* optr = P.dec;
         const uint32_t* tab = s_tab;
+        const uint8_t* lens_row = s_lens;
         uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
         if (item < nitems) {
             const int c = (int)(item / P.item_chunks), j = (int)(item % P.item_chunks);
@@ -121,6 +144,7 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                         sbase = P.stream + (size_t)c * P.slot_bytes;
                         optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
                         tab += (size_t)en << Wv;
+                        lens_row += en * 16;
                         const uint4 mp = reinterpret_cast<const uint4*>(s_map)[pk];
                         m0 = mp.x; m1 = mp.y; m2 = mp.z; m3 = mp.w;
                     }
@@ -128,10 +152,8 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
             }
         }
         int done = 0;                                            // symbols already written out
-        unsigned long long queue = 0;                            // decoded symbols not yet in the tile, one per byte
-        uint32_t fill8 = 0;                                      // 8 x their number (0, 8, 16, 24)
         while (__any_sync(FULL, rem > 0)) {
-            // ---- stage 272 stream bytes per lane (one TMA bulk copy each), from the 16-byte unit holding `bitpos` ----
+            // ---- stage one period's stream bytes per lane (one TMA bulk copy each), from the 16-byte unit holding `bitpos` ----
             uint32_t cur_al = (bitpos >> 7) << 4;
             if (rem > 0 && cur_al >= slot_bytes) {               // ran past the slot (corrupt stream): drop the rest of the chunk
                 dec_flag(P.status, MUA_DEC_BAD_OFFSET);
@@ -158,38 +180,47 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
             uint32_t consumed = 0;                               // bits consumed in this stage
 
             for (int per = 0; per < periods_per_stage && __any_sync(FULL, rem > 0); ++per) {
-                // ---- 128 symbols per lane into the output tile ----
-                uint32_t* orow = reinterpret_cast<uint32_t*>(s_out + lane * DG_OUT_B);
-                uint32_t wpos = 0;                               // words of this period's tile row already written
-                while (__any_sync(FULL, wpos < 32)) {
-                    const bool act = wpos < 32;
-                    const uint32_t x = __funnelshift_l(lo, hi, off);
-                    const uint32_t e = tab[x >> wshift];
-                    uint32_t syms;
-                    if (!WIDE) {
-                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(syms) : "r"(m0), "r"(m1), "r"(e));
+                // ---- 128 symbols per lane into the output tile: 16 steps of 8 symbols = two table lookups ----
+                // A lookup returns as many whole symbols as its Wv-bit window holds, at most 4.  The common case -- both
+                // lookups of a step return 4 (the frequent MUA counts code in 1..2 bits) -- has fixed output positions and no
+                // per-symbol work: the second lookup is issued speculatively at the bit offset the first one reports.  When
+                // any lane of the warp meets a window with fewer than 4 symbols, the step is redone quad by quad: the entry's
+                // symbols are kept and the rest of the quad is decoded one symbol at a time through the same table (first
+                // symbol of the entry at the running offset, length from the row's SCLV).
+                uint2* orow = reinterpret_cast<uint2*>(s_out + lane * DG_OUT_B);
+#pragma unroll 2
+                for (int q = 0; q < 16; ++q) {
+                    const uint32_t x = __funnelshift_l(lo, hi, off);             // next 32 stream bits, first one at bit 31
+                    const uint32_t eA = tab[x >> wshift];
+                    const uint32_t uA = (eA >> 20) & 0xFu;
+                    const uint32_t eB = tab[(x << uA) >> wshift];
+                    uint32_t sA = dv_syms<WIDE>(eA, m0, m1, m2, m3), sB = dv_syms<WIDE>(eB, m0, m1, m2, m3);
+                    uint32_t used = uA + ((eB >> 20) & 0xFu);
+                    const bool esc = ((eA & eB) & 0x40000u) == 0u && q * 8 < rem;   // count field [18:16] == 4 <=> bit 18
+                    if (__any_sync(FULL, esc)) {
+                        uint32_t e = eA;
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t xx = __funnelshift_l(lo, hi, off);
+                            uint32_t u = (e >> 20) & 0xFu;
+                            uint32_t syms = dv_syms<WIDE>(e, m0, m1, m2, m3);
+                            for (uint32_t j = (e >> 16) & 7u; j < 4u; ++j) {       // per-lane trip count 0..3
+                                const uint32_t r = tab[(xx << u) >> wshift] & 0xFu; // first symbol of the entry at the running offset
+                                syms |= dv_syms<WIDE>(r | (WIDE ? 0xFFF0u : 0x8880u), m0, m1, m2, m3) << (8u * j);
+                                u += lens_row[r];
+                            }
+                            if (h == 0) sA = syms; else sB = syms;
+                            off += u;                                              // <= 32 bits per quad: one refill suffices
+                            consumed += u;
+                            if (off >= 32u) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(STR_W - 1))]); ++rp; off -= 32u; }
+                            e = tab[__funnelshift_l(lo, hi, off) >> wshift];       // entry of the second quad at its true offset
+                        }
                     } else {
-                        uint32_t slo, shi, msk;
-                        const uint32_t e7 = e & 0x7777u;
-                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(slo) : "r"(m0), "r"(m1), "r"(e7));
-                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(shi) : "r"(m2), "r"(m3), "r"(e7));
-                        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(msk) : "r"(0x0000FF00u), "r"(0u), "r"((e >> 3) & 0x1111u));
-                        syms = (slo & ~msk) | (shi & msk);
+                        off += used;
+                        consumed += used;
+                        if (off >= 32u) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(STR_W - 1))]); ++rp; off -= 32u; }
                     }
-                    syms = act ? syms : 0u;
-                    const uint32_t cnt8 = act ? (e >> 13) & 0x38u : 0u;
-                    const uint32_t used = act ? (e >> 20) & 0xFu : 0u;
-                    queue |= (unsigned long long)syms << fill8;
-                    fill8 += cnt8;
-                    if (fill8 >= 32) {
-                        orow[wpos] = (uint32_t)queue;
-                        ++wpos;
-                        queue >>= 32;
-                        fill8 -= 32;
-                    }
-                    off += used;
-                    consumed += used;
-                    if (off >= 32) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(STR_W - 1))]); ++rp; off -= 32; }
+                    orow[q] = make_uint2(sA, sB);
                 }
                 __syncwarp();
                 // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----

@@ -598,6 +598,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
 //     bit offsets; every piece is OR-ed into a zeroed staging ring with shared-memory atomics -- words that are
 //     all zero (the common codeword of the most frequent symbol is '0') are not touched at all; the flush writes
 //     complete 128-bit units with coalesced 16-byte stores and re-zeroes what it has read.
+#ifndef MUA_EP_DENSE
+#define MUA_EP_DENSE 1                   // register placement for tiles whose lanes all code <= 64 bits per chunk (else: atomics)
+#endif
 constexpr int EP_NG = 2;                 // 1024-symbol chunks per warp tile
 constexpr int EP_TILE = EP_NG * TILE;
 constexpr int EP_NST = 2;                // TMA stages per warp
@@ -698,6 +701,41 @@ __device__ __forceinline__ uint32_t enc_pair_tile(const uint8_t* tile, uint32_t 
     const uint32_t excl = incl - nbp;
     const uint32_t tot0 = tot & 0xFFFFu;
     uint32_t pos[EP_NG] = {Pbits + (excl & 0xFFFFu), Pbits + tot0 + (excl >> 16)};
+#if MUA_EP_DENSE
+    // Register placement (the fast encoder's): in a full tile every symbol codes >= 1 bit, so a lane's 32 symbols of a chunk
+    // are >= 32 bits and complete at least one word; when they are also <= 64 bits in EVERY lane (warp vote -- true for nearly
+    // every tile of MUA counts, whose frequent symbols code in 1..2 bits) the four pieces of a chunk are merged into one 64-bit
+    // register, shifted to their bit offset with funnel shifts and stored as whole words: the partial word between two lanes
+    // travels by one shuffle, between the two chunks of the tile by another.  No atomics, no data-dependent branches.  The ring
+    // keeps the protocol of the atomic path (zero ahead of the stream, the open word lives in the ring), so the two paths mix.
+    if (FULLT && __all_sync(FULL, ((nbp & 0xFFFFu) <= 64u) & ((nbp >> 16) <= 64u))) {
+        uint32_t incoming = (Pbits & 31u) ? s_ring[(Pbits >> 5) & RM] : 0u;     // the stream's open word (broadcast read)
+#pragma unroll
+        for (int g = 0; g < EP_NG; ++g) {
+            unsigned long long acc = oc[4 * g];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) acc = (acc << ol[4 * g + j]) | oc[4 * g + j];
+            const uint32_t nb = (nbp >> (16 * g)) & 0xFFFFu;                     // 32..64
+            const uint32_t sh = pos[g] & 31u, wi = pos[g] >> 5;
+            const unsigned long long A = acc << (64u - nb);
+            const uint32_t Ahi = (uint32_t)(A >> 32), Alo = (uint32_t)A;
+            const uint32_t W0 = Ahi >> sh;
+            const uint32_t W1 = __funnelshift_r(Alo, Ahi, sh);
+            const uint32_t W2 = __funnelshift_r(0u, Alo, sh);
+            const uint32_t e = sh + nb;                                          // 32..95: one or two complete words
+            const bool two = e >= 64u;
+            const uint32_t tail = (e & 31u) ? (two ? W2 : W1) : 0u;
+            uint32_t inc = __shfl_up_sync(FULL, tail, 1);
+            if (lane == 0) inc = incoming;
+            incoming = __shfl_sync(FULL, tail, 31);
+            s_ring[wi & RM] = W0 | inc;
+            if (two) s_ring[(wi + 1) & RM] = W1;
+        }
+        Pbits += tot0 + (tot >> 16);
+        if (lane == 0 && (Pbits & 31u)) s_ring[(Pbits >> 5) & RM] = incoming;    // the new open word
+        return tot0;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 4 * EP_NG; ++i) {
         // zero bits need no write (the ring is zero); an empty piece has oc == 0, so its shift amount does not matter

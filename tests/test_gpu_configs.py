@@ -117,7 +117,7 @@ def test_result_pickles_feed_analysis_consumers(recordings, tmp_path):
     g = load_golden("br_approx_sort.npz")
     res = D.br_script(all_binned, bin_vector, True, seed=int(g["seed"]))
     names = D.save_br_results(res, str(tmp_path))
-    assert len(names) == 54 and os.path.basename(names[0]) == "BRs_S_10_BP_1_CV_1.pkl"
+    assert len(names) == 54 and os.path.basename(names[0]) == "BRs_S_2_BP_1_CV_1.pkl"
     hist_bits = [2 ** e for e in range(2, 11)]
     CV = 1
     formatted, want_formatted = [], []
