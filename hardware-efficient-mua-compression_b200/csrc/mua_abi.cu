@@ -601,8 +601,8 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
 #ifndef MUA_DL_NC
 #define MUA_DL_NC 1
 #endif
-#ifndef MUA_DV_PPS
-#define MUA_DV_PPS 1          // 128-symbol periods per staged stream row of k_decode_var
+#ifndef MUA_DV_EXTRA
+#define MUA_DV_EXTRA 256      // bits a staged stream row of k_decode_var holds beyond one worst-case period
 #endif
             constexpr int NC = MUA_DL_NC;
             cudaError_t e = cudaFuncSetAttribute(k_decode_lane<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
@@ -630,9 +630,11 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
         }
     } else {
         // variable-count lookups from per-row rank tables in shared memory: one persistent CTA per SM
-        const int fixed = 4 * MUA_MAX_S * 4 + 16 + DV_LENS_B + (h.K << h.Wv) * 4;      // rank maps, ticket, SCLV rows, tables
-        P.var_pps = MUA_DV_PPS;
-        P.var_str_w = ((127 + 64 + P.var_pps * 131 * h.Lmax + 31) / 32 + 3) / 4 * 4;     // whole 16-byte units
+        const int fixed = 4 * MUA_MAX_S * 4 + 16 + DV_LENS_B + h.K * ((1 << h.Wv) + DV_ROW_SKEW) * 4;      // rank maps, ticket, SCLV rows, tables
+        // staged stream row per lane: alignment slack + one worst-case period + look-ahead + MUA_DV_EXTRA bits (a stage serves
+        // periods for as long as a worst-case period still fits: ~MUA_DV_EXTRA / 130 more periods of typical MUA counts)
+        P.var_pps = 1;
+        P.var_str_w = ((127 + 96 + 128 * h.Lmax + MUA_DV_EXTRA + 31) / 32 + 3) / 4 * 4;     // whole 16-byte units
         const int DV_PER_WARP = 32 * P.var_str_w * 4 + 32 * DG_OUT_B + 16;
         int nw = (227 * 1024 - fixed) / DV_PER_WARP;
         nw = nw > DV_WARPS ? DV_WARPS : nw;

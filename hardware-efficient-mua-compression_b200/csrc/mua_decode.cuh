@@ -31,6 +31,9 @@ constexpr int DG_OUT_B = 144;         // output tile row of the general decoder:
 // offset lies past its slot (an encode that overflowed, or corrupt side info): the chunk is skipped, nothing outside the
 // stream buffer is read; MUA_DEC_BAD_TABLE = the table block does not match the S/K/Lmax the host passed, or a channel's
 // peak >= S / SCLV row >= K: nothing (or not that channel) is decoded.
+// little-endian word of the stream -> stream bit j at register bit j
+__device__ __forceinline__ uint32_t stream_rev(uint32_t w) { return __byte_perm(__brev(w), 0, 0x0123); }
+
 __device__ __forceinline__ void dec_flag(int32_t* status, int code) {
     if (status) atomicMax(status, code);
 }
@@ -67,6 +70,7 @@ __device__ __forceinline__ uint32_t dv_syms(uint32_t e, uint32_t m0, uint32_t m1
 
 constexpr int DV_WARPS = 20;            // at most; the launch takes as many as fit beside the tables
 constexpr int DV_LENS_B = (MUA_MAX_K * 16 + 127) / 128 * 128;
+constexpr int DV_ROW_SKEW = 11;         // words between the tables of two codebook rows beyond 2^Wv (bank skew)
 
 template <bool WIDE>
 __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_constant__ DecParams P) {
@@ -94,20 +98,29 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
     if (threadIdx.x == 0) *s_ticket = 0;
     {
         const uint32_t* g = reinterpret_cast<const uint32_t*>(P.tab + T->decv_off);
-        for (int i = threadIdx.x; i < (K << Wv); i += blockDim.x) s_tab[i] = g[i];
+        // entry of window v of row k at word k * (2^Wv + DV_ROW_SKEW) + bitreverse(v): the index is the window with its FIRST
+        // stream bit in bit 0, so the bank of a lookup is decided by the first five bits of the window (the symbols being
+        // decoded) and rows are skewed against each other -- the all-zero window of every row and the windows with one early
+        // non-zero symbol, which make up most lookups of MUA counts, fall into different banks (54 % of the shared wavefronts
+        // were bank conflicts with the window's LAST bits as bank index)
+        for (int i = threadIdx.x; i < (K << Wv); i += blockDim.x) {
+            const int k = i >> Wv, v = i & ((1 << Wv) - 1);
+            s_tab[k * ((1 << Wv) + DV_ROW_SKEW) + (int)(__brev((uint32_t)v) >> (32 - Wv))] = g[i];
+        }
         const uint32_t* gi = reinterpret_cast<const uint32_t*>(&T->idx[0][0]);
         for (int i = threadIdx.x; i < 4 * MUA_MAX_S; i += blockDim.x) s_map[i] = gi[i];
         for (int i = threadIdx.x; i < K * 16; i += blockDim.x) s_lens[i] = T->lens[i >> 4][i & 15];
     }
     __syncthreads();
     uint32_t parity = 0;
-    // a period decodes 128 symbols and may run up to 3 symbols ahead (they wait in the register queue); the host sized
-    // the staged row for var_pps periods: 127 bits of alignment slack + var_pps * 131 * Lmax + 64 bits of look-ahead
-    const int periods_per_stage = P.var_pps;
+    // the host sized the staged row: 127 bits of alignment slack + one worst-case period (128 * Lmax bits) + 96 bits of look-ahead
+    // + var_extra bits; a stage is decoded period by period for as long as every lane still holds a worst-case period
+    const uint32_t need_bits = 128u * (uint32_t)T->Lmax + 96u;
     const long long nitems = (long long)P.C * P.item_chunks;
     const long long ngroups = (nitems + 31) / 32;
     const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
-    const uint32_t wshift = 32 - Wv;
+    const uint32_t wmask = (1u << Wv) - 1u;
+    const int row_words = (1 << Wv) + DV_ROW_SKEW;
 
     // groups by ticket (the warps of a CTA do not sit evenly on the four schedulers): ticket t = group blockIdx + t * grid
     for (;;) {
@@ -143,7 +156,7 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                         bitpos = bp0;
                         sbase = P.stream + (size_t)c * P.slot_bytes;
                         optr = P.dec + (P.off ? P.off[c] : (int64_t)c * P.stride) + a;
-                        tab += (size_t)en << Wv;
+                        tab += en * row_words;
                         lens_row += en * 16;
                         const uint4 mp = reinterpret_cast<const uint4*>(s_map)[pk];
                         m0 = mp.x; m1 = mp.y; m2 = mp.z; m3 = mp.w;
@@ -171,15 +184,18 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                 mbar_wait(s_bar, parity);
                 parity ^= 1;
             }
-            const uint32_t* rowp = s_str + lane * STR_W;
             const uint32_t boff = bitpos - cur_al * 8;           // 0..127
-            uint32_t rp = boff >> 5;
-            uint32_t hi = bswap32(rowp[rp]), lo = bswap32(rowp[rp + 1]);
+            const uint32_t* rp = s_str + lane * STR_W + (boff >> 5);
+            // the stream is kept bit-reversed: stream bit j of a word at register bit j, w0 = the word holding the position
+            uint32_t w0 = stream_rev(rp[0]), w1 = stream_rev(rp[1]);
             rp += 2;
             uint32_t off = boff & 31;
             uint32_t consumed = 0;                               // bits consumed in this stage
+            // this lane can decode another period from the staged row while a worst-case period (+ look-ahead) is still inside
+            // it -- or the row already reaches the end of the slot
+            const uint32_t staged_bits = (cur_al + nbytes >= slot_bytes) ? 0xFFFFFFFFu : nbytes * 8u;
 
-            for (int per = 0; per < periods_per_stage && __any_sync(FULL, rem > 0); ++per) {
+            for (bool more = true; more;) {
                 // ---- 128 symbols per lane into the output tile: 16 steps of 8 symbols = two table lookups ----
                 // A lookup returns as many whole symbols as its Wv-bit window holds, at most 4.  The common case -- both
                 // lookups of a step return 4 (the frequent MUA counts code in 1..2 bits) -- has fixed output positions and no
@@ -190,10 +206,10 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                 uint2* orow = reinterpret_cast<uint2*>(s_out + lane * DG_OUT_B);
 #pragma unroll 2
                 for (int q = 0; q < 16; ++q) {
-                    const uint32_t x = __funnelshift_l(lo, hi, off);             // next 32 stream bits, first one at bit 31
-                    const uint32_t eA = tab[x >> wshift];
+                    const uint32_t x = __funnelshift_r(w0, w1, off);             // next 32 stream bits, first one at bit 0
+                    const uint32_t eA = tab[x & wmask];
                     const uint32_t uA = (eA >> 20) & 0xFu;
-                    const uint32_t eB = tab[(x << uA) >> wshift];
+                    const uint32_t eB = tab[(x >> uA) & wmask];
                     uint32_t sA = dv_syms<WIDE>(eA, m0, m1, m2, m3), sB = dv_syms<WIDE>(eB, m0, m1, m2, m3);
                     uint32_t used = uA + ((eB >> 20) & 0xFu);
                     const bool esc = ((eA & eB) & 0x40000u) == 0u && q * 8 < rem;   // count field [18:16] == 4 <=> bit 18
@@ -201,24 +217,26 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                         uint32_t e = eA;
 #pragma unroll 1
                         for (int h = 0; h < 2; ++h) {
-                            const uint32_t xx = __funnelshift_l(lo, hi, off);
-                            uint32_t u = (e >> 20) & 0xFu;
                             uint32_t syms = dv_syms<WIDE>(e, m0, m1, m2, m3);
-                            for (uint32_t j = (e >> 16) & 7u; j < 4u; ++j) {       // per-lane trip count 0..3
-                                const uint32_t r = tab[(xx << u) >> wshift] & 0xFu; // first symbol of the entry at the running offset
+                            uint32_t u = (e >> 20) & 0xFu;                         // the entry's symbols: <= Wv bits
+                            uint32_t j = (e >> 16) & 7u;
+                            for (;;) {                                             // per-lane trip count 1..4
+                                off += u;
+                                consumed += u;
+                                if (off >= 32u) { w0 = w1; w1 = stream_rev(*rp); ++rp; off -= 32u; }
+                                if (j >= 4u) break;
+                                const uint32_t r = tab[__funnelshift_r(w0, w1, off) & wmask] & 0xFu;   // first symbol at the running offset
                                 syms |= dv_syms<WIDE>(r | (WIDE ? 0xFFF0u : 0x8880u), m0, m1, m2, m3) << (8u * j);
-                                u += lens_row[r];
+                                u = lens_row[r];
+                                ++j;
                             }
                             if (h == 0) sA = syms; else sB = syms;
-                            off += u;                                              // <= 32 bits per quad: one refill suffices
-                            consumed += u;
-                            if (off >= 32u) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(STR_W - 1))]); ++rp; off -= 32u; }
-                            e = tab[__funnelshift_l(lo, hi, off) >> wshift];       // entry of the second quad at its true offset
+                            e = tab[__funnelshift_r(w0, w1, off) & wmask];         // entry of the second quad at its true offset
                         }
                     } else {
                         off += used;
                         consumed += used;
-                        if (off >= 32u) { hi = lo; lo = bswap32(rowp[min(rp, (uint32_t)(STR_W - 1))]); ++rp; off -= 32u; }
+                        if (off >= 32u) { w0 = w1; w1 = stream_rev(*rp); ++rp; off -= 32u; }
                     }
                     orow[q] = make_uint2(sA, sB);
                 }
@@ -243,6 +261,7 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                 }
                 __syncwarp();
                 if (rem > 0) { rem -= 128; done += 128; }
+                more = __any_sync(FULL, rem > 0) && __all_sync(FULL, rem <= 0 || boff + consumed + need_bits <= staged_bits);
             }
             bitpos += consumed;
             if (rem <= 0) rem = 0;
@@ -498,8 +517,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-// little-endian word of the stream -> stream bit j at register bit j
-__device__ __forceinline__ uint32_t stream_rev(uint32_t w) { return __byte_perm(__brev(w), 0, 0x0123); }
 
 // One lane's stream ring: 128 bytes, byte b of the stream (counted from the ring origin, a 32-byte aligned
 // address at or before the chunk's first bit) lives at ring offset b mod 128.  The ring is topped up with two

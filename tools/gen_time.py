@@ -22,8 +22,9 @@ def timeit(fn, n=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 t_enc = timeit(lambda: P.encode(rec, cb, st, en, pk, ec, out=es))
-t_dec = timeit(lambda: P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=64 + T // 2))
+status = torch.zeros(1, dtype=torch.int32, device="cuda")
+t_dec = timeit(lambda: P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=64 + T // 2, status=status))
 nsym = int((en - st).clamp(min=0).sum().item()); bits = int(es.total_bits.sum().item())
-ok = int(P.verify(rec, dec, S, st, en).item()) == 0
+ok = int(P.verify(rec, dec, S, st, en).item()) == 0 and int(status.item()) == 0
 print(json.dumps({"S": S, "BP": BP, "encode_ms": t_enc, "encode_GBs": (nsym + bits / 8) / t_enc / 1e6, "decode_ms": t_dec,
                   "decode_GBs": (nsym + bits / 8) / t_dec / 1e6, "bits_per_symbol": bits / nsym, "parity_ok": ok}))

@@ -24,7 +24,7 @@ for r in rows:
             line = (cur_file, int(r[0]))
             src[line] = r[1]
         if r[ci].isdigit():
-            agg[line][0] += int(r[ci]); agg[line][1] += int(r[sm] or 0)
+            agg[line][0] += int(r[ci]); agg[line][1] += int(r[sm]) if r[sm].isdigit() else 0
 tot = sum(v[0] for v in agg.values()); tots = sum(v[1] for v in agg.values())
 print("total instr %d, samples %d" % (tot, tots))
 for line, (n, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
