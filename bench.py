@@ -321,7 +321,7 @@ def run_b200(a):
     comm = torch.cuda.Stream(device=dev) if report_mode == "nccl" else None
     torch.cuda.synchronize()
     step_no = [0]
-    launches_per_step = 3 + (2 if peer is not None else 0)       # k_calibrate*, k_encode*, k_decode* (+ k_report_signal, k_report_wait)
+    launches_per_step = 3       # k_calibrate*, k_encode*, k_decode* (p2p: the encoder signals the report, the decoder waits for it)
 
     def step(ev=None):
         step_no[0] += 1
@@ -330,8 +330,6 @@ def run_b200(a):
         st, en, pk, ec = sel("cutoff"), sel("end"), sel("peak"), sel("enc")
         if ev: ev[1].record()
         P.encode(rec, cb, st, en, pk, ec, out=es, sink=peer.sink(k) if peer is not None else None)
-        if peer is not None:
-            peer.signal(k)
         if ev: ev[2].record()
         rep = None
         if report_mode == "nccl":
@@ -339,12 +337,14 @@ def run_b200(a):
             comm.wait_stream(main)
             with torch.cuda.stream(comm):
                 rep = D.gather_channel_report(es.total_bits, en - st, ec, pk, C_total, out=rep_buf, dtype=rep_dtype)
-        P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=max_end, status=dec_status)
+        # p2p: the decoder's first block ends by polling the report flags (all set long before: the peers signalled at the end
+        # of their encode), so the step needs no fourth launch
+        P.decode(es, rec, cb, st, en, pk, ec, out=dec, max_end=max_end, status=dec_status,
+                 wait_sink=peer.sink(k, signal=False) if peer is not None else None, wait_step=k if peer is not None else 0)
         if ev: ev[3].record()
         if report_mode == "nccl":
             main.wait_stream(comm)
         elif peer is not None:
-            peer.wait(k)
             rep = k
         if ev: ev[4].record()
         return rep
@@ -389,7 +389,8 @@ def run_b200(a):
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     total_ms = evs[0][0].elapsed_time(t_end)
-    stage_ms = np.array([[evs[k][i].elapsed_time(evs[k][i + 1]) for i in range(4)] for k in range(a.steps)]).mean(axis=0)
+    stage_all = np.array([[evs[k][i].elapsed_time(evs[k][i + 1]) for i in range(4)] for k in range(a.steps)])
+    stage_ms = stage_all.mean(axis=0)
     if world > 1:
         tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -455,7 +456,9 @@ def run_b200(a):
               "encode_frac": enc_bytes / stage_ms[1] / 1e6 / peak_gbs, "decode_frac": dec_bytes / stage_ms[2] / 1e6 / peak_gbs,
               "combined_gbs": (enc_bytes + dec_bytes) / (stage_ms[1] + stage_ms[2]) / 1e6,
               "combined_frac": (enc_bytes + dec_bytes) / (stage_ms[1] + stage_ms[2]) / 1e6 / peak_gbs,
-              "bits_per_symbol": bits_local / max(nsym_local, 1)}
+              "bits_per_symbol": bits_local / max(nsym_local, 1),
+              "per_step_ms": {"calibrate": [round(float(v), 4) for v in stage_all[:, 0]], "encode": [round(float(v), 4) for v in stage_all[:, 1]],
+                              "decode": [round(float(v), 4) for v in stage_all[:, 2]], "gather": [round(float(v), 4) for v in stage_all[:, 3]]}}
     names = W["kernels"]
     order = np.argsort([-stage_ms[0], -stage_ms[1], -stage_ms[2]])
     di = int(order[0])
@@ -486,10 +489,10 @@ def run_b200(a):
             "data": "synthetic", "config": cfg,
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * a.steps,
-            "launches_per_step": {"own_kernels": launches_per_step, "kernels": names + (["k_report_signal", "k_report_wait"] if peer is not None else []),
+            "launches_per_step": {"own_kernels": launches_per_step, "kernels": names,
                                   "other": "none" if report_mode != "nccl" else "torch stack/cast kernels + NCCL all_gather on the side stream"},
             "report": {"mode": report_mode, "verified": report_verified, "fallback_reason": peer_err,
-                       "what": {"p2p": "rows stored by the encoder into every peer's buffer over NVLink, flag poll after the decode",
+                       "what": {"p2p": "rows stored by the encoder into every peer's buffer over NVLink, its last block signals the step, the decoder's first block ends by polling the flags",
                                 "nccl": "all_gather_into_tensor on a side stream", "none": "single GPU"}[report_mode]},
             "report_verified": report_verified,
             "clocks": clocks, "BR_bits_per_s_per_channel": float(br["BR"]), "lossless": True,

@@ -30,7 +30,8 @@ IPC_HANDLE_BYTES = 64
 
 class ReportSink(C.Structure):
     """struct mua_report_sink (include/mua_b200.h): every peer's report buffer and flag block."""
-    _fields_ = [("n_peers", _i32), ("rank", _i32), ("row0", _i64), ("d_report", _vp * MAX_PEERS), ("d_flags", _vp * MAX_PEERS)]
+    _fields_ = [("n_peers", _i32), ("rank", _i32), ("row0", _i64), ("signal_step", _i32), ("reserved", _i32),
+                ("d_report", _vp * MAX_PEERS), ("d_flags", _vp * MAX_PEERS)]
 
 
 #: every symbol include/mua_b200.h declares -> (restype, argtypes)
@@ -60,7 +61,7 @@ SIGNATURES = {
     "mua_report_signal": (C.c_int, [_vp, _i32, _vp]),
     "mua_report_wait": (C.c_int, [_vp, _i32, _vp]),
     "mua_decode": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                             _i32, _vp, _vp, _vp]),
+                             _i32, _vp, _vp, _vp, _i32, _vp]),
     "mua_verify": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mua_online_histogram": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "mua_approx_sort": (C.c_int, [_vp, C.c_int, _i32, _i64, _vp, _vp]),

@@ -457,13 +457,10 @@ int mua_report_signal(const mua_report_sink* h_sink, int32_t step, void* stream)
 int mua_report_wait(const mua_report_sink* h_sink, int32_t step, void* stream) {
     int rc = check_sink(h_sink);
     if (rc) return rc;
-    int khz = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
     PeerFlags F;
     F.n = h_sink->n_peers; F.rank = h_sink->rank;
     for (int i = 0; i < MUA_MAX_PEERS; ++i) F.flags[i] = i < F.n ? h_sink->d_flags[i] : nullptr;
-    k_report_wait<<<1, 32, 0, (cudaStream_t)stream>>>(F, step, (long long)(khz > 0 ? khz : 1500000) * 2000ll);
+    k_report_wait<<<1, 32, 0, (cudaStream_t)stream>>>(F, step, 2000000000ll);   // give up after 2 s (%globaltimer, ns)
     CHECK_LAUNCH("k_report_wait");
     return MUA_OK;
 }
@@ -489,8 +486,8 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax;
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
     P.total_bits = d_total_bits; P.overflow = d_overflow;
-    P.n_peers = 0; P.row0 = 0;
-    for (int i = 0; i < MUA_MAX_PEERS; ++i) P.rep[i] = nullptr;
+    P.n_peers = 0; P.row0 = 0; P.signal_step = 0; P.rank = 0;
+    for (int i = 0; i < MUA_MAX_PEERS; ++i) { P.rep[i] = nullptr; P.flags[i] = nullptr; }
     if (h_sink && h_sink->n_peers > 0) {
         REQUIRE(h_sink->n_peers <= MUA_MAX_PEERS && h_sink->row0 >= 0, "bad report sink");
         REQUIRE((long long)T * Lmax < (1ll << 31), "report sink rows are int32: T * Lmax must be < 2^31");
@@ -500,6 +497,15 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         }
         P.n_peers = h_sink->n_peers;
         P.row0 = h_sink->row0;
+        if (h_sink->signal_step > 0) {
+            REQUIRE(h_sink->rank >= 0 && h_sink->rank < h_sink->n_peers, "report sink: bad rank");
+            for (int i = 0; i < h_sink->n_peers; ++i) {
+                REQUIRE(h_sink->d_flags[i], "report sink: d_flags[%d] is NULL", i);
+                P.flags[i] = h_sink->d_flags[i];
+            }
+            P.signal_step = h_sink->signal_step;
+            P.rank = h_sink->rank;
+        }
     }
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
     if (h.Lmax <= 2 && S <= 4) {
@@ -571,7 +577,7 @@ int mua_pack_streams(const uint8_t* d_stream, int64_t slot_bytes, const int64_t*
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off, int32_t chunk_stride, const int64_t* d_off,
                int64_t stride, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
                const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end, uint8_t* d_dec,
-               int32_t* d_status, void* stream) {
+               int32_t* d_status, const mua_report_sink* h_wait_sink, int32_t wait_step, void* stream) {
     REQUIRE(C >= 0, "C < 0");
     if (C == 0) return MUA_OK;                                  // nothing to decode: per-channel arrays may be empty (NULL)
     REQUIRE(d_stream && d_chunk_off && d_start && d_end && d_peak && d_enc && d_tables && d_dec && d_status, "NULL argument");
@@ -588,6 +594,12 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
     P.off = d_off; P.stride = stride; P.C = C; P.S = S; P.start = d_start; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
     P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax; P.dec = d_dec; P.status = d_status;
+    P.wait_flags = nullptr; P.wait_n = 0; P.wait_step = 0;
+    if (h_wait_sink && h_wait_sink->n_peers > 0 && wait_step > 0) {
+        int rcs = check_sink(h_wait_sink);
+        if (rcs) return rcs;
+        P.wait_flags = h_wait_sink->d_flags[h_wait_sink->rank]; P.wait_n = h_wait_sink->n_peers; P.wait_step = wait_step;
+    }
     REQUIRE(slot_bytes < (1ll << 32), "slot_bytes must be < 4 GiB");
     // chunks per channel that can be non-empty: ceil(max_end / CHUNK) when the caller bounds the window end
     P.item_chunks = chunk_stride;
@@ -635,6 +647,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
         // periods for as long as a worst-case period still fits: ~MUA_DV_EXTRA / 130 more periods of typical MUA counts)
         P.var_pps = 1;
         P.var_str_w = ((127 + 96 + 128 * h.Lmax + MUA_DV_EXTRA + 31) / 32 + 3) / 4 * 4;     // whole 16-byte units
+        if ((P.var_str_w / 4) % 2 == 0) P.var_str_w += 4;     // row stride = 16 B x odd: the lanes' refill words spread over 8 banks (a 128-byte stride puts all 32 lanes on one)
         const int DV_PER_WARP = 32 * P.var_str_w * 4 + 32 * DG_OUT_B + 16;
         int nw = (227 * 1024 - fixed) / DV_PER_WARP;
         nw = nw > DV_WARPS ? DV_WARPS : nw;

@@ -67,8 +67,11 @@ __host__ __device__ inline int rank_of(int p, int s, int S) {
 }
 
 // window of the variable-count decode tables: as wide as keeps K tables within 64 KB (72 KB for S = 10), 9..12 bits
+#ifndef MUA_DV_WMAX
+#define MUA_DV_WMAX 12
+#endif
 __host__ __device__ inline int decv_window(int K, int Lmax) {
-    int W = 12;
+    int W = MUA_DV_WMAX;
     while (W > 9 && (long long)K * (1ll << W) * 4 > 64 * 1024) --W;
     return W < Lmax ? Lmax : W;
 }

@@ -22,6 +22,10 @@ struct DecParams {
     int32_t K, Lmax;
     uint8_t* dec;
     int32_t* status;            // see dec_flag
+    // fused report wait (mua_report_sink passed to mua_decode): block 0 ends by polling the own flag block until every rank
+    // has signalled wait_step -- the decode that follows an encode then also guarantees the gathered report, with no extra launch
+    const int32_t* wait_flags;
+    int32_t wait_n, wait_step;
     int32_t var_str_w, var_pps;   // k_decode_var: staged stream words per lane and stage, 128-symbol periods per stage
 };
 
@@ -33,6 +37,25 @@ constexpr int DG_OUT_B = 144;         // output tile row of the general decoder:
 // peak >= S / SCLV row >= K: nothing (or not that channel) is decoded.
 // little-endian word of the stream -> stream bit j at register bit j
 __device__ __forceinline__ uint32_t stream_rev(uint32_t w) { return __byte_perm(__brev(w), 0, 0x0123); }
+
+__device__ __forceinline__ void dec_wait_report(const DecParams& P) {
+    if (P.wait_n > 0 && blockIdx.x == 0 && (int)threadIdx.x < P.wait_n) {
+        const int32_t* f = P.wait_flags + threadIdx.x;
+        long long t0 = 0;
+        for (unsigned it = 0;; ++it) {
+            int32_t v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v >= P.wait_step) break;
+            long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (it == 0) t0 = t;
+            if (t - t0 > 2000000000ll) {                       // 2 s: give up, leave the sticky marker k_report_wait leaves
+                const_cast<int32_t*>(P.wait_flags)[MUA_MAX_PEERS] = 1;
+                break;
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ void dec_flag(int32_t* status, int code) {
     if (status) atomicMax(status, code);
@@ -68,7 +91,10 @@ __device__ __forceinline__ uint32_t dv_syms(uint32_t e, uint32_t m0, uint32_t m1
     return syms;
 }
 
-constexpr int DV_WARPS = 20;            // at most; the launch takes as many as fit beside the tables
+#ifndef MUA_DV_WARPS
+#define MUA_DV_WARPS 20
+#endif
+constexpr int DV_WARPS = MUA_DV_WARPS;            // at most; the launch takes as many as fit beside the tables
 constexpr int DV_LENS_B = (MUA_MAX_K * 16 + 127) / 128 * 128;
 constexpr int DV_ROW_SKEW = 11;         // words between the tables of two codebook rows beyond 2^Wv (bank skew)
 
@@ -101,8 +127,9 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
         // entry of window v of row k at word k * (2^Wv + DV_ROW_SKEW) + bitreverse(v): the index is the window with its FIRST
         // stream bit in bit 0, so the bank of a lookup is decided by the first five bits of the window (the symbols being
         // decoded) and rows are skewed against each other -- the all-zero window of every row and the windows with one early
-        // non-zero symbol, which make up most lookups of MUA counts, fall into different banks (54 % of the shared wavefronts
-        // were bank conflicts with the window's LAST bits as bank index)
+        // non-zero symbol, which make up most lookups of MUA counts, fall into different banks.  (Folding the upper index bits
+        // onto the low five as well -- idx ^ idx >> 5 ^ idx >> 10, so that windows whose first five bits are zero leave bank 0
+        // too -- cuts the remaining conflicts but its three instructions sit on the lookup chain: 2.08 -> 2.19 ms, rejected.)
         for (int i = threadIdx.x; i < (K << Wv); i += blockDim.x) {
             const int k = i >> Wv, v = i & ((1 << Wv) - 1);
             s_tab[k * ((1 << Wv) + DV_ROW_SKEW) + (int)(__brev((uint32_t)v) >> (32 - Wv))] = g[i];
@@ -203,7 +230,8 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                 // any lane of the warp meets a window with fewer than 4 symbols, the step is redone quad by quad: the entry's
                 // symbols are kept and the rest of the quad is decoded one symbol at a time through the same table (first
                 // symbol of the entry at the running offset, length from the row's SCLV).
-                uint2* orow = reinterpret_cast<uint2*>(s_out + lane * DG_OUT_B);
+                uint4* orow = reinterpret_cast<uint4*>(s_out + lane * DG_OUT_B);
+                uint32_t sA0 = 0, sB0 = 0;                       // symbols of the even step: the tile takes 16 bytes at a time
 #pragma unroll 2
                 for (int q = 0; q < 16; ++q) {
                     const uint32_t x = __funnelshift_r(w0, w1, off);             // next 32 stream bits, first one at bit 0
@@ -231,14 +259,16 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                                 ++j;
                             }
                             if (h == 0) sA = syms; else sB = syms;
-                            e = tab[__funnelshift_r(w0, w1, off) & wmask];         // entry of the second quad at its true offset
+                            e = tab[__funnelshift_r(w0, w1, off) & wmask];  // entry of the second quad at its true offset
                         }
                     } else {
                         off += used;
                         consumed += used;
                         if (off >= 32u) { w0 = w1; w1 = stream_rev(*rp); ++rp; off -= 32u; }
                     }
-                    orow[q] = make_uint2(sA, sB);
+                    // 16-byte stores: with the 144-byte row stride a quarter warp covers all 32 banks (8-byte stores conflict 2-way)
+                    if (q & 1) orow[q >> 1] = make_uint4(sA0, sB0, sA, sB);
+                    else { sA0 = sA; sB0 = sB; }
                 }
                 __syncwarp();
                 // ---- coalesced write-out: 8 lanes per row, 4 rows per pass ----
@@ -267,6 +297,7 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
             if (rem <= 0) rem = 0;
         }
     }
+    dec_wait_report(P);
 }
 
 // ---- fast decoder (NSYM = 4: codebooks with Lmax <= 2) ----
@@ -415,6 +446,7 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
             optr += DF_PER;
         }
     }
+    dec_wait_report(P);
 }
 
 // ---- fast decoder with lane-private LUT banks (NSYM = 4, W = 8, K <= 3, S <= 8: the chosen system) ----
@@ -785,6 +817,7 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
         g = gn;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    dec_wait_report(P);
 }
 
 // ---- round-trip check: dec == min(sym, S-1) on [start, end) ------------------------------------

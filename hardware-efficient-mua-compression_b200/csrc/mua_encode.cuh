@@ -35,6 +35,9 @@ struct EncParams {
     int32_t n_peers;
     int64_t row0;
     int32_t* rep[MUA_MAX_PEERS];
+    // signal_step > 0: the last block to retire tells every peer that this rank's rows of that step are written
+    int32_t signal_step, rank;
+    int32_t* flags[MUA_MAX_PEERS];
 };
 
 // Channel epilogue of every encoder: the bit count for the local caller and -- when a report sink is attached -- the channel's
@@ -46,6 +49,30 @@ __device__ __forceinline__ void publish_channel(const EncParams& P, int c, uint3
     if (lane < P.n_peers) {
         const int4 row = make_int4((int)Pbits, max(end - start, 0), en, pk);
         *reinterpret_cast<int4*>(P.rep[lane] + 4 * (P.row0 + c)) = row;
+    }
+}
+
+// End of an encoder block when the sink asks for the signal: every warp makes its peer stores visible system-wide, the block's
+// last thread through the barrier counts the block in; the block that completes the count publishes the step to every peer
+// (what k_report_signal does as a separate launch) and re-arms the counter.
+__device__ __forceinline__ void signal_when_last(const EncParams& P) {
+    if (P.signal_step <= 0) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int32_t* counter = P.flags[P.rank] + MUA_MAX_PEERS + 1;
+        int last = 0;
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+        }
+        last = __shfl_sync(FULL, last, 0);
+        if (last) {
+            __threadfence_system();
+            if (threadIdx.x == 0) *counter = 0;
+            if ((int)threadIdx.x < P.n_peers)
+                asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(P.flags[threadIdx.x] + P.rank), "r"(P.signal_step) : "memory");
+        }
     }
 }
 
@@ -402,6 +429,7 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
         }
         publish_channel(P, c, Pbits, start, end, pk_c, en_c, lane);
     }
+    signal_when_last(P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -581,6 +609,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_gen(const __grid_c
         }
         publish_channel(P, c, Pbits, start, end, pk_c, en_c, lane);
     }
+    signal_when_last(P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -866,6 +895,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
         }
         publish_channel(P, c, Pbits, start, end, pk_c, en_c, lane);
     }
+    signal_when_last(P);
 }
 
 
@@ -887,21 +917,26 @@ __global__ void k_report_signal(const __grid_constant__ PeerFlags F, int32_t ste
     }
 }
 
-// lane p polls the flag of source rank p in the OWN flag block; gives up after `max_cycles` (sticky marker in slot MUA_MAX_PEERS)
-__global__ void k_report_wait(const __grid_constant__ PeerFlags F, int32_t step, long long max_cycles) {
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// lane p polls the flag of source rank p in the OWN flag block; gives up after `max_ns` (sticky marker in slot MUA_MAX_PEERS)
+__global__ void k_report_wait(const __grid_constant__ PeerFlags F, int32_t step, long long max_ns) {
     const int p = threadIdx.x;
     if (p < F.n) {
         const int32_t* f = F.flags[F.rank] + p;
-        const long long t0 = clock64();
+        const long long t0 = global_ns();
         int32_t v;
         for (;;) {
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
             if (v >= step) break;
-            if (clock64() - t0 > max_cycles) {
+            if (global_ns() - t0 > max_ns) {
                 F.flags[F.rank][MUA_MAX_PEERS] = 1;
                 break;
             }
-            __nanosleep(200);
         }
     }
 }

@@ -102,7 +102,7 @@ class PeerReport:
     buffers int32 [C_total, 4] (alternated by step parity) and a flag block in one cudaMalloc'd, IPC-exported allocation;
     all ranks map each other's allocation (cudaIpcOpenMemHandle, NVLink peer access).  The encoder (pipeline.encode(sink=...))
     stores each channel's row {bits, symbols, SCLV row, peak} into all ranks' buffers in its channel epilogue;
-    `signal(step)` after the encoder publishes "my rows are written", `wait(step)` -- enqueued where the report is needed,
+    the encoder's last block (or a separate `signal(step)` launch) publishes "my rows are written", `wait(step)` -- enqueued where the report is needed,
     e.g. after the round-trip decode -- returns on the stream once every rank's rows of that step have landed.
 
     One process per GPU of one node; the handles travel through torch.distributed (all_gather_object)."""
@@ -147,9 +147,12 @@ class PeerReport:
             self._sinks.append(s)
         dist.barrier(group=group)                       # every rank has mapped every buffer before anyone stores into them
 
-    def sink(self, step):
-        """the sink of step `step` (1, 2, ...): pass to pipeline.encode"""
-        return self._sinks[step & 1]
+    def sink(self, step, signal=True):
+        """the sink of step `step` (1, 2, ...): pass to pipeline.encode.  signal=True: the encoder itself publishes the step to
+        the peers when its last block retires (no `signal` launch needed)."""
+        s = self._sinks[step & 1]
+        s.signal_step = int(step) if signal else 0
+        return s
 
     def _stream(self):
         return self._C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -293,14 +293,16 @@ _DEC_STATUS = {_lib.DEC_BAD_OFFSET: "a chunk's bit offset lies past its slot (en
 
 
 def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, enc, out: torch.Tensor = None,
-           max_end: int = 0, status: torch.Tensor = None):
+           max_end: int = 0, status: torch.Tensor = None, wait_sink=None, wait_step: int = 0):
     """Stage 6 (mua_decode): symbols written back at their absolute bin index into a buffer with the
     layout of `rec.sym` (bytes outside the window are left as they were; a fresh buffer is zeroed).
     max_end: host-known upper bound of `end` (0 = unknown); it only trims the launch.
     status : int32 [1] device tensor that receives the decoder's status word (include/mua_b200.h MUA_DEC_*).  Without it
              the call is CHECKED: it refuses streams whose encode flagged an overflow / table mismatch and raises if the
              decoder reports one (one device synchronisation).  Pass a tensor to stay asynchronous (the caller zeroes and
-             reads it; `check_decode_status`)."""
+             reads it; `check_decode_status`).
+    wait_sink, wait_step: multi-GPU report sink (dist.PeerReport): the kernel also waits until every rank's report rows of
+             that step have landed (instead of a separate PeerReport.wait launch)."""
     lib = _lib.load()
     checked = status is None
     if checked:
@@ -318,7 +320,8 @@ def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, e
     with torch.cuda.device(rec.device):
         _lib.check(lib.mua_decode(_ptr(es.stream), es.slot_bytes, _ptr(es.chunk_off), es.chunk_stride, _ptr(rec.off),
                                   int(rec.stride), rec.C, cb.S, _ptr(start), _ptr(end), _ptr(peak), _ptr(enc),
-                                  _ptr(cb.d_tables), cb.K, cb.Lmax, int(max_end), _ptr(out), _ptr(status), _stream()))
+                                  _ptr(cb.d_tables), cb.K, cb.Lmax, int(max_end), _ptr(out), _ptr(status),
+                                  C.byref(wait_sink) if wait_sink is not None else None, int(wait_step), _stream()))
     if checked:
         check_decode_status(status)
     return out

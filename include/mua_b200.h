@@ -192,7 +192,8 @@ int mua_elim_scores(const uint8_t* d_enc, const int64_t* d_min1, const int64_t* 
  *   mua_peer_open    map another process's buffer (cudaIpcOpenMemHandle, peer access enabled lazily); mua_peer_close unmaps.
  *   mua_peer_free    cudaFree of an own buffer.
  *   mua_report_signal  enqueue after mua_encode: rank `sink->rank` tells every peer "my rows of step `step` are written"
- *                    (system-scope release store of `step` into d_flags[peer][rank]).
+ *                    (system-scope release store of `step` into d_flags[peer][rank]).  Not needed when the sink passed to
+ *                    mua_encode carries signal_step > 0: then the encoder's last block to retire does the same stores.
  *   mua_report_wait  enqueue where the report is needed: returns (on the stream) once d_flags[rank][p] >= step for every peer
  *                    p; gives up after ~2 s and stores 1 into d_flags[rank][MUA_MAX_PEERS] instead of hanging the device.
  * Steps are numbered 1, 2, ...; callers alternate two report buffers by step parity, so a peer that is one step ahead
@@ -201,8 +202,12 @@ typedef struct mua_report_sink {
     int32_t n_peers;                       /* ranks sharing the report (<= MUA_MAX_PEERS); 0 = no sink */
     int32_t rank;                          /* this process's index */
     int64_t row0;                          /* global index of this rank's first channel */
+    int32_t signal_step;                   /* mua_encode only: > 0 = the encoder itself signals this step when its last
+                                              block retires (no mua_report_signal launch needed); 0 = it does not */
+    int32_t reserved;
     int32_t* d_report[MUA_MAX_PEERS];      /* int32 [C_total][4] on every peer (entry `rank` = the own buffer) */
-    int32_t* d_flags[MUA_MAX_PEERS];       /* int32 [MUA_MAX_PEERS + 1] on every peer: [p] = last step signalled by rank p */
+    int32_t* d_flags[MUA_MAX_PEERS];       /* int32 [MUA_MAX_PEERS + 2] on every peer: [p] = last step signalled by rank p,
+                                              [MUA_MAX_PEERS] = wait timed out, [MUA_MAX_PEERS + 1] = block counter (zero it once) */
 } mua_report_sink;
 int mua_peer_alloc(size_t bytes, void** d_ptr, uint8_t* h_handle);
 int mua_peer_open(const uint8_t* h_handle, void** d_ptr);
@@ -247,12 +252,16 @@ int mua_pack_streams(const uint8_t* d_stream, int64_t slot_bytes, const int64_t*
  * only sizes the launch (chunks past it are never scheduled).
  * d_status: int32 [1], zeroed by the caller; MUA_DEC_BAD_OFFSET / MUA_DEC_BAD_TABLE (the larger one wins) when
  * something was not decoded -- a decode after an encode that set MUA_ENC_OVERFLOW reports MUA_DEC_BAD_OFFSET
- * for the chunks that start past the slot and garbage-free output cannot be assumed for the truncated channel. */
+ * for the chunks that start past the slot and garbage-free output cannot be assumed for the truncated channel.
+ * h_wait_sink / wait_step: NULL / 0, or the multi-GPU report sink: the decode's first block ends by polling the own flag
+ * block until every rank has signalled `wait_step` (what mua_report_wait does as a separate launch), so a round-trip decode
+ * that follows the encode also completes the gathered report. */
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off,
                int32_t chunk_stride, const int64_t* d_off, int64_t stride, int32_t C, int32_t S,
                const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
                const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end,
-               uint8_t* d_dec, int32_t* d_status, void* stream);
+               uint8_t* d_dec, int32_t* d_status, const mua_report_sink* h_wait_sink, int32_t wait_step,
+               void* stream);
 
 /* Round-trip check on the device: counts positions in [start,end) where d_dec != min(d_sym, S-1).
  * d_mismatch : uint64 [1] (zeroed by the call). */

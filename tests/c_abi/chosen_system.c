@@ -70,7 +70,7 @@ int main(void) {
     CK(mua_encode(d_sym, NULL, NULL, stride, T, C, S, d_cut, d_end, d_peak, d_enc, d_tab, K, 2, d_stream, slot, d_co,
                   chunk_stride, d_bits, d_ovf, NULL, NULL));
     CK(mua_decode(d_stream, slot, d_co, chunk_stride, NULL, stride, C, S, d_cut, d_end, d_peak, d_enc, d_tab, K, 2,
-                  H + T / 2, d_dec, d_ovf + 1, NULL));
+                  H + T / 2, d_dec, d_ovf + 1, NULL, 0, NULL));
     CK(mua_verify(d_sym, d_dec, NULL, stride, C, S, d_cut, d_end, d_mis, NULL));
     CU(cudaDeviceSynchronize());
 

@@ -115,7 +115,7 @@ def test_table_and_channel_state_mismatch_is_reported(sclv_tables):
         dec.fill_(0xEE)
         _lib.check(lib.mua_decode(es.stream.data_ptr(), es.slot_bytes, es.chunk_off.data_ptr(), es.chunk_stride, None, rec.stride, C, S,
                                   st.data_ptr(), en.data_ptr(), peak.data_ptr(), enc.data_ptr(), cb.d_tables.data_ptr(), K, Lmax, 0,
-                                  dec.data_ptr(), status.data_ptr(), None))
+                                  dec.data_ptr(), status.data_ptr(), None, 0, None))
         return int(status.item())
 
     assert raw_decode(cb.K, cb.Lmax, pk, ec) == 0 and int(P.verify(rec, dec, S, st, en).item()) == 0
