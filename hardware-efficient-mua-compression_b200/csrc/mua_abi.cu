@@ -68,9 +68,9 @@ void layout_sizes(int S, int K, int Lmax, TabHdr* h) {
     h->enc2_off = align_up(h->enc1_off + S * K * 16 * 4, 512);
     int next = align_up(h->enc2_off + S * K * 256 * 4, 512);
     h->enc4_off = 0;
-    if (Lmax <= 2) {
+    if (Lmax <= 2 && S <= 3) {
         h->enc4_off = next;
-        next = align_up(next + S * K * 256 * 2, 512);
+        next = align_up(next + S * K * 768, 512);
     }
     h->encp_off = 0;
     if (Lmax <= 8) {
@@ -508,9 +508,9 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         }
     }
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
-    if (h.Lmax <= 2 && S <= 4) {
+    if (h.Lmax <= 2 && S <= 3) {
         const int smem = EncFastSmem::PER_WARP * EF_WARPS;
-        const int per_sm = EF_NG == 2 ? 4 : 5;
+        const int per_sm = 4;
         const int need = (C + EF_WARPS - 1) / EF_WARPS;
         const int grid = need < sm_count() * per_sm ? need : sm_count() * per_sm;
 #define MUA_LAUNCH_ENC(SV)                                                                                          \
@@ -520,8 +520,7 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         k_encode_fast<SV><<<grid, EF_WARPS * 32, smem, st>>>(P);                                                    \
     } while (0)
         if (S == 2) MUA_LAUNCH_ENC(2);
-        else if (S == 3) MUA_LAUNCH_ENC(3);
-        else MUA_LAUNCH_ENC(4);
+        else MUA_LAUNCH_ENC(3);
 #undef MUA_LAUNCH_ENC
     } else if (h.Lmax <= 8 && S >= 3 && S <= 9) {
         const int smem = EncPairSmem::PER_WARP * ENC_WARPS;

@@ -39,19 +39,37 @@ __global__ void __launch_bounds__(256) k_build_tables(uint8_t* __restrict__ blob
         uint32_t l1 = s_len[r1];
         enc2[tid] = (((uint32_t)s_code[r0] << l1) | s_code[r1]) | (((uint32_t)s_len[r0] + l1) << 24);
     }
-    if (T->enc4_off && tid < S * S * S * S) {   // Lmax <= 2 (S <= 4): four saturated symbols per entry, index in base S
-        uint8_t* enc4 = blob + T->enc4_off + (size_t)(p * K + k) * 512;   // [0,256): codes, [256,512): lengths
-        uint32_t code = 0, len = 0;
-        int rest = tid;
+    if (T->enc4_off) {   // Lmax <= 2 and S <= 3: four saturated symbols per entry (fast encoder), 768 bytes per (peak, row) pair
+        uint8_t* enc4 = blob + T->enc4_off + (size_t)(p * K + k) * 768;
+        if (tid < S * S * S * S) {                    // full tiles: index in base S -> codes [0,128), lengths [128,256)
+            uint32_t code = 0, len = 0;
+            int rest = tid;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = s_rank[rest % S];
-            rest /= S;
-            code = (code << s_len[r]) | s_code[r];
-            len += s_len[r];
+            for (int i = 0; i < 4; ++i) {
+                const int r = s_rank[rest % S];
+                rest /= S;
+                code = (code << s_len[r]) | s_code[r];
+                len += s_len[r];
+            }
+            enc4[tid] = (uint8_t)code;
+            enc4[128 + tid] = (uint8_t)len;
         }
-        enc4[tid] = (uint8_t)code;
-        enc4[256 + tid] = (uint8_t)len;
+        if (tid < (S + 1) * (S + 1) * (S + 1) * (S + 1)) {   // partial tiles: index in base S+1, digit S = outside the window, no bits
+            uint32_t code = 0, len = 0;                      // -> codes [256,512), lengths [512,768)
+            int rest = tid;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = rest % (S + 1);
+                rest /= (S + 1);
+                if (q < S) {
+                    const int r = s_rank[q];
+                    code = (code << s_len[r]) | s_code[r];
+                    len += s_len[r];
+                }
+            }
+            enc4[256 + tid] = (uint8_t)code;
+            enc4[512 + tid] = (uint8_t)len;
+        }
     }
     if (T->encp_off && tid < (S + 1) * (S + 1)) {   // Lmax <= 8: symbol pairs, index in base S+1 (digit S = no symbol)
         uint8_t* encp = blob + T->encp_off + (size_t)(p * K + k) * 512;

@@ -13,9 +13,10 @@ constexpr int TILE = MUA_CHUNK;        // symbols per warp tile == decode chunk
 // ---- device table block (built by k_build_tables) ------------------------------------------
 // enc1 : uint32 [S][K][16]    raw nibble b -> (len << 16 | code) of rank[p][min(b,S-1)]
 // enc2 : uint32 [S][K][256]   raw nibble pair (b0 | b1<<4), b0 first in time -> code | len << 24   (general encoder)
-// enc4 : uint8  [S][K][2][256] four saturated symbols, index in base S (q0 + S*q1 + S^2*q2 + S^3*q3, q0 first in
-//                             time; S^4 <= 256 entries: 81 B for S=3 = one word per bank, conflict-free)
-//                             -> [0][i] = code (<= 8 bits), [1][i] = length; only when Lmax <= 2 (fast encoder)
+// enc4 : [S][K] x 768 B       four saturated symbols per entry, only when Lmax <= 2 and S <= 3 (fast encoder):
+//                             [0,128) codes and [128,256) lengths indexed in base S (q0 + S*q1 + S^2*q2 + S^3*q3, q0 first
+//                             in time; S^4 <= 81 entries = one word per bank, conflict-free); [256,512) codes and [512,768)
+//                             lengths indexed in base S+1, digit S = "outside the window" without bits (partial tiles)
 // encp : [S][K] x 512 B      two saturated symbols (or the null symbol S = "outside the window": no bits), index
 //                             i = q1 + (S+1)*q0 (q0 first in time): uint16 code at byte 2i, uint8 length at byte
 //                             256 + 2i; only when Lmax <= 8 (pair encoder)
@@ -140,6 +141,12 @@ __device__ __forceinline__ int warp_sum(int v) {
 __device__ __forceinline__ uint32_t ge_mask(uint32_t w, uint32_t lo7, int v) {
     return ((lo7 + (uint32_t)(0x80 - v) * 0x01010101u) | w) & 0x80808080u;
 }
+
+// volatile loads: issued where they are written (the compiler would otherwise sink them to their first use)
+__device__ __forceinline__ int ldg_s32(const int32_t* p) { int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (int)v; }
+__device__ __forceinline__ long long ldg_s64(const int64_t* p) { long long v; asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
 
 // counter-based RNG of the synthetic generator (mirrors oracle/mua_oracle.py:_mix32)
 __host__ __device__ inline uint32_t mix32(uint32_t x) {

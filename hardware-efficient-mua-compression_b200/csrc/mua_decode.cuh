@@ -498,12 +498,6 @@ struct DecItem {
     int pk, en;              // peak (rank -> symbol map) and codebook row (table)
 };
 
-// volatile loads: issued where they are written (the compiler would otherwise sink them to their first use)
-__device__ __forceinline__ int ldg_s32(const int32_t* p) { int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ int ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (int)v; }
-__device__ __forceinline__ long long ldg_s64(const int64_t* p) { long long v; asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
-
 __device__ __forceinline__ DecRaw dec_load(const DecParams& P, long long item, long long nitems) {
     DecRaw r;
     r.valid = item < nitems;

@@ -136,24 +136,31 @@ __device__ __forceinline__ void flush_last(const uint32_t* s_ring, uint8_t* out,
 }
 
 // ---------------------------------------------------------------------------------------------
-// fast encoder (Lmax <= 2): EF_NG groups of 32 symbols per lane and tile
+// fast encoder (Lmax <= 2, S <= 3): 64 symbols per lane and 2048-symbol tile
 // ---------------------------------------------------------------------------------------------
-#ifndef MUA_EF_NG
-#define MUA_EF_NG 2
-#endif
-constexpr int EF_NG = MUA_EF_NG;       // 32-symbol groups per lane: 2 -> 2048-symbol tiles, 4 -> 4096-symbol tiles
-constexpr int ETILE = EF_NG * TILE;    // symbols per warp tile of the fast encoder (EF_NG decode chunks)
+// Tiles start at the window (origin = start rounded down to 64 symbols, one lane's share), not at absolute multiples of the
+// tile size: every tile but the last is a full tile (and the first one when the window starts off a 64-symbol boundary).
+// The last tile is coded with as few 16-symbol pieces per lane as cover what is left of the window (1..4, warp-uniform):
+// a 1 200-symbol window costs 3 pieces per lane, not a whole 2048-symbol tile.  Partial tiles use a second table whose
+// base-(S+1) index has a null digit without bits for symbols outside the window (SWAR range mask), so they run the code
+// of a full tile -- no per-symbol loops.  The 1024-symbol chunks of the side info stay aligned to ABSOLUTE bin indices (the
+// stream format does not change): in a full tile a chunk starts with the first symbol of a lane; in a partial tile it falls on
+// a 16-symbol piece boundary inside some lane, whose bit offset is the lane's plus the lengths of its pieces before it.
+static_assert(TILE == 1024, "chunk arithmetic below assumes 1024-symbol chunks");
+static_assert(TILE == 1024, "chunk arithmetic below assumes 1024-symbol chunks");
+constexpr int EF_NG = 2;               // 32-symbol groups per lane
+constexpr int ETILE = EF_NG * TILE;    // symbols per warp tile of the fast encoder (two decode chunks)
 constexpr int EF_NST = 2;              // TMA stages per warp
-constexpr int EF_WARPS = EF_NG == 2 ? 8 : 4;   // warps per CTA
+constexpr int EF_WARPS = 8;            // warps per CTA
+constexpr int EF_LUT_B = 768;          // per (peak, row) pair: base-S codes [0,128) + lengths [128,256), null-digit codes [256,512) + lengths [512,768)
 
 struct EncFastSmem {
-    static constexpr int RW = EF_NG == 2 ? 256 : 512;           // staging ring words (2*ETILE bits per tile + slack)
+    static constexpr int RW = 256;                              // staging ring words (2*ETILE bits per tile + slack)
     static constexpr int IN = 0;                                // EF_NST * ETILE bytes
-    static constexpr int LUT4 = IN + EF_NST * ETILE;            // 256 * 2, 512-byte aligned
-    static constexpr int LUT1 = LUT4 + 512;                     // 16 * 4
-    static constexpr int RING = LUT1 + 64;                      // RW * 4
+    static constexpr int LUT = IN + EF_NST * ETILE;             // EF_LUT_B bytes, 256-byte aligned
+    static constexpr int RING = LUT + EF_LUT_B;                 // RW * 4
     static constexpr int BARS = RING + RW * 4;                  // EF_NST * 8
-    static constexpr int PER_WARP = (BARS + EF_NST * 8 + 511) / 512 * 512;
+    static constexpr int PER_WARP = (BARS + EF_NST * 8 + 255) / 256 * 256;
 };
 
 // inclusive warp scan: shfl.up with its in-range predicate feeding a predicated add (2 instructions/step)
@@ -171,11 +178,13 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u8_256(uint32_t saddr) {   // same index, second table (+256 bytes)
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u8_at(uint32_t saddr) {   // same index, second table (+OFF bytes)
     uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1+256];" : "=r"(v) : "r"(saddr));
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u8_256(uint32_t saddr) { return lds_u8_at<256>(saddr); }
 
 // 16 symbols (one uint4) -> code bits (right aligned, <= 32) and bit count (16..32).  The kernel is bound by the
 // ALU pipe, so the per-word work is cut to 3 ALU ops (+2 on the FMA pipe, 2 byte loads):
@@ -185,9 +194,12 @@ __device__ __forceinline__ uint32_t lds_u8_256(uint32_t saddr) {   // same index
 //   p   = ws * gmul           (FMA pipe)  gathers them into the top byte in base S: q0 + S*q1 + S^2*q2 + S^3*q3
 //                                         (gmul = S^3 | S^2<<8 | S<<16 | 1<<24; no carries: every partial sum < 256)
 //   adr = prmt(p, lut)        (ALU)       LUT base (256-byte aligned) with its low byte replaced by the index
-//   code = lut[adr], len = lut[adr + 256] (two byte loads: no unpacking)
-__device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uint32_t satk, uint32_t satv, uint32_t gmul,
-                                         uint32_t& code, uint32_t& len) {
+//   code = lut[adr], len = lut[adr + 128] (two byte loads: no unpacking; S^4 <= 81 entries: one word per bank)
+template <int SV>
+__device__ __forceinline__ void encode16(const uint4 q, uint32_t lut_saddr, uint32_t& code, uint32_t& len) {
+    constexpr uint32_t satk = (uint32_t)(0x7F - (SV - 1)) * 0x01010101u;   // SWAR saturation constants
+    constexpr uint32_t satv = (uint32_t)(SV - 1) * 0x01010101u;
+    constexpr uint32_t gmul = (uint32_t)(SV * SV * SV) | ((uint32_t)(SV * SV) << 8) | ((uint32_t)SV << 16) | (1u << 24);
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t qc[4], ql[4];
 #pragma unroll
@@ -195,9 +207,40 @@ __device__ __forceinline__ void encode16(const uint4 q, uint32_t lut4_saddr, uin
         const uint32_t g = w[j] + satk;
         const uint32_t m = byte_msb_mask(g);
         const uint32_t ws = (w[j] & ~m) | (satv & m);
-        const uint32_t adr = __byte_perm(ws * gmul, lut4_saddr, 0x7653);
+        const uint32_t adr = __byte_perm(ws * gmul, lut_saddr, 0x7653);
         qc[j] = lds_u8(adr);
-        ql[j] = lds_u8_256(adr);
+        ql[j] = lds_u8_at<128>(adr);
+    }
+    qc[0] = (qc[0] << ql[1]) | qc[1]; ql[0] += ql[1];
+    qc[2] = (qc[2] << ql[3]) | qc[3]; ql[2] += ql[3];
+    code = (qc[0] << ql[2]) | qc[2];
+    len = ql[0] + ql[2];
+}
+
+// Same for a piece of a partial tile: symbols whose index in the lane (i0 .. i0+15) lies outside [vlo, vhi) become the
+// null digit S of the base-(S+1) table at lutn_saddr (= the pair's table block + 256) and code no bits: 0..32 bits.
+template <int SV>
+__device__ __forceinline__ void encode16n(const uint4 q, uint32_t lutn_saddr, uint32_t i0, uint32_t vlo4, uint32_t vhi4, uint32_t& code,
+                                          uint32_t& len) {
+    constexpr uint32_t satk = (uint32_t)(0x7F - (SV - 1)) * 0x01010101u;
+    constexpr uint32_t satv = (uint32_t)(SV - 1) * 0x01010101u;
+    constexpr uint32_t nullv = (uint32_t)SV * 0x01010101u;
+    constexpr int B = SV + 1;
+    constexpr uint32_t gmul = (uint32_t)(B * B * B) | ((uint32_t)(B * B) << 8) | ((uint32_t)B << 16) | (1u << 24);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t qc[4], ql[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t g = w[j] + satk;
+        const uint32_t m = byte_msb_mask(g);
+        uint32_t ws = (w[j] & ~m) | (satv & m);
+        const uint32_t iv = (0x83828180u + 0x04040404u * (uint32_t)j) + i0 * 0x01010101u;   // symbol indices of this word, bit 7 set (< 64)
+        const uint32_t ok = (iv - vlo4) & ~(iv - vhi4);                                      // bit 7: vlo <= index < vhi
+        const uint32_t vm = byte_msb_mask(ok);
+        ws = (ws & vm) | (nullv & ~vm);
+        const uint32_t adr = __byte_perm(ws * gmul, lutn_saddr, 0x7653);
+        qc[j] = lds_u8(adr);
+        ql[j] = lds_u8_at<256>(adr);
     }
     qc[0] = (qc[0] << ql[1]) | qc[1]; ql[0] += ql[1];
     qc[2] = (qc[2] << ql[3]) | qc[3]; ql[2] += ql[3];
@@ -213,17 +256,13 @@ __device__ __forceinline__ uint4 clamp127(uint4 q) {
     return q;
 }
 
-// One tile of the fast encoder.  FULLT: the whole tile lies inside the window (every 32-symbol group emits
-// 32..64 bits).  The lane's 32*NG bytes are 2*NG 16-byte pieces; with a lane stride of 32*NG bytes, reading
-// piece k in every lane would be a bank conflict, so lane l reads piece (k + rot) mod 2NG (rot from the lane
-// index: conflict-free) and a log2(2NG)-level select network puts the results back in order.
-template <bool FULLT, uint32_t RM, int NG>
-__device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4_saddr, const uint32_t* s_lut1, uint32_t satk,
-                                              uint32_t satv, uint32_t gmul, int ts, int start, int end, int lane, uint32_t* s_ring,
-                                              uint32_t& Pbits, uint32_t& carry, uint32_t& a_lane) {
-    constexpr int NP = 2 * NG;
-    const uint32_t rot = NG == 2 ? ((lane >> 1) & 3) : (lane & 7);
-    uint32_t pc[NP], pl[NP];
+// The four 16-symbol pieces of a lane in a full tile.  The lane's 64 bytes are four 16-byte pieces; with a lane stride
+// of 64 bytes, reading piece k in every lane would be a bank conflict, so lane l reads piece (k + rot) mod 4 (rot from the
+// lane index: conflict-free) and a two-level select network puts the results back in order.
+template <int SV>
+__device__ __forceinline__ void enc_fast_pieces(const uint8_t* tile, uint32_t lut_saddr, int lane, uint32_t (&pc)[4], uint32_t (&pl)[4]) {
+    constexpr int NP = 4;
+    const uint32_t rot = (lane >> 1) & 3;
     uint4 qv[NP];
     uint32_t any_hi = 0;
 #pragma unroll
@@ -236,7 +275,7 @@ __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4
         for (int k = 0; k < NP; ++k) qv[k] = clamp127(qv[k]);
     }
 #pragma unroll
-    for (int k = 0; k < NP; ++k) encode16(qv[k], lut4_saddr, satk, satv, gmul, pc[k], pl[k]);
+    for (int k = 0; k < NP; ++k) encode16<SV>(qv[k], lut_saddr, pc[k], pl[k]);
 #pragma unroll
     for (int lev = 1; lev < NP; lev <<= 1) {
         const bool r = rot & lev;
@@ -246,37 +285,54 @@ __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4
 #pragma unroll
         for (int j = 0; j < NP; ++j) { pc[j] = tc[j]; pl[j] = tl4[j]; }
     }
+}
+
+// The pieces of a lane in a partial tile: lane l holds symbols [16 k l, 16 k (l + 1)) of the tile, k = pieces per lane (1..4,
+// warp-uniform); symbols outside the window code no bits; pieces >= k are empty.
+template <int SV>
+__device__ __forceinline__ void enc_fast_pieces_partial(const uint8_t* tile_w, uint32_t lutn_saddr, int ts, int start, int end, int k, int lane,
+                                                        uint32_t (&pc)[4], uint32_t (&pl)[4]) {
+    const uint8_t* lp = tile_w + lane * 16 * k;
+    const int p0 = ts + lane * 16 * k;                                  // absolute index of the lane's first symbol
+    const uint32_t vlo4 = (uint32_t)min(max(start - p0, 0), 64) * 0x01010101u;   // valid symbols of this lane: [vlo, vhi)
+    const uint32_t vhi4 = (uint32_t)min(max(end - p0, 0), 64) * 0x01010101u;
+    uint4 qv[4];
+    uint32_t any_hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        qv[i] = make_uint4(0, 0, 0, 0);
+        if (i < k) {
+            qv[i] = *reinterpret_cast<const uint4*>(lp + 16 * i);
+            any_hi |= (qv[i].x | qv[i].y) | (qv[i].z | qv[i].w);
+        }
+    }
+    if (__any_sync(FULL, (any_hi & 0x80808080u) != 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qv[i] = clamp127(qv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pc[i] = 0; pl[i] = 0;
+        if (i < k) encode16n<SV>(qv[i], lutn_saddr, 16u * i, vlo4, vhi4, pc[i], pl[i]);
+    }
+}
+
+// Bit offsets and placement of a tile's pieces (piece lengths in stream order).  FULLT: every 32-symbol group of every lane
+// emits 32..64 bits.  Complete words go to the staging ring; the lane's first complete word waits for the partial word of the
+// lanes before it (one shuffle in a full tile, a segmented OR-scan when some lanes complete no word).
+template <bool FULLT, uint32_t RM>
+__device__ __forceinline__ void enc_fast_place(const uint32_t (&pc)[4], const uint32_t (&pl)[4], int lane, uint32_t* s_ring, uint32_t& Pbits,
+                                               uint32_t& carry, uint32_t& a_lane) {
+    constexpr int NG = 2;
     unsigned long long acc[NG];
     uint32_t nb[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         acc[g] = ((unsigned long long)pc[2 * g] << pl[2 * g + 1]) | pc[2 * g + 1];
-        nb[g] = pl[2 * g] + pl[2 * g + 1];                          // 32..64 bits
-    }
-    if (!FULLT) {
-        // head/tail tile: a group outside the window emits nothing; a group cut by the window boundary is
-        // recoded symbol by symbol (at most two such groups per channel)
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int p0 = ts + lane * (32 * NG) + g * 32;
-            const int vlo = max(start - p0, 0), vhi = min(end - p0, 32);
-            if (vlo > 0 || vhi < 32) {
-                unsigned long long ac = 0;
-                uint32_t n1 = 0;
-                for (int i = vlo; i < vhi; ++i) {
-                    const uint32_t e1 = s_lut1[min((uint32_t)tile[g * 32 + i], 15u)];
-                    ac = (ac << (e1 >> 16)) | (e1 & 0xFFFFu);
-                    n1 += e1 >> 16;
-                }
-                acc[g] = ac;
-                nb[g] = n1;
-            }
-        }
+        nb[g] = pl[2 * g] + pl[2 * g + 1];                          // full tile: 32..64 bits
     }
     // ---- bit offsets ----
-    uint32_t nbt = 0;
-#pragma unroll
-    for (int g = 0; g < NG; ++g) nbt += nb[g];
+    const uint32_t nbt = nb[0] + nb[1];
     const uint32_t incl = warp_incl_scan_p(nbt);
     const uint32_t Pnew = Pbits + __shfl_sync(FULL, incl, 31);
     const uint32_t a = Pbits + incl - nbt;
@@ -320,23 +376,23 @@ __device__ __forceinline__ void enc_fast_tile(const uint8_t* tile, uint32_t lut4
     Pbits = Pnew;
 }
 
-template <int SV>   // alphabet size as a compile-time constant: the SWAR constants and the gather multiplier become immediates
-__global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fast(const __grid_constant__ EncParams P) {
+template <int SV>   // alphabet size as a compile-time constant: the SWAR constants and the gather multipliers are immediates
+__global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_constant__ EncParams P) {
+    static_assert(SV == 2 || SV == 3, "the null-digit table needs (S+1)^4 <= 256 entries");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = EncFastSmem;
     constexpr uint32_t RM = SM::RW - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* sm = smem_raw + warp * SM::PER_WARP;
     uint8_t* s_in = sm + SM::IN;
-    const uint32_t lut4_saddr = smem_u32(sm + SM::LUT4);          // 512-byte aligned: OR-able with idx*2
-    uint32_t* s_lut1 = reinterpret_cast<uint32_t*>(sm + SM::LUT1);
+    const uint32_t lut_saddr = smem_u32(sm + SM::LUT);            // 256-byte aligned: the index replaces its low byte
     uint32_t* s_ring = reinterpret_cast<uint32_t*>(sm + SM::RING);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm + SM::BARS);
 
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K;
     constexpr int S = SV;
-    if (T->S != SV || S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || S > 4 || T->enc4_off == 0 || (lut4_saddr & 255u)) {
+    if (T->S != SV || S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 2 || T->enc4_off == 0 || (lut_saddr & 255u)) {
         if (threadIdx.x == 0) *P.overflow = MUA_ENC_BAD_TABLE;   // launch configuration does not match the table block
         return;
     }
@@ -346,11 +402,7 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
         fence_barrier_init();
     }
     __syncwarp();
-    const uint32_t* g_enc1 = reinterpret_cast<const uint32_t*>(P.tab + T->enc1_off);
     const uint4* g_enc4 = reinterpret_cast<const uint4*>(P.tab + T->enc4_off);
-    constexpr uint32_t satk = (uint32_t)(0x7F - (S - 1)) * 0x01010101u;   // SWAR saturation constants
-    constexpr uint32_t satv = (uint32_t)(S - 1) * 0x01010101u;
-    constexpr uint32_t gmul = (uint32_t)(S * S * S) | ((uint32_t)(S * S) << 8) | ((uint32_t)S << 16) | (1u << 24);
     const uint32_t slot_units = (uint32_t)min((long long)(P.slot_bytes >> 4), 0x7FFFFFFFll);
 
     const int gwarp = blockIdx.x * EF_WARPS + warp, nwarps = gridDim.x * EF_WARPS;
@@ -367,19 +419,25 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
             if (lane == 0) *P.overflow = MUA_ENC_BAD_TABLE;
         } else if (end > start && start >= 0) {
             const int combo = pk_c * K + en_c;
-            if (combo != cur_combo) {   // this (peak, codebook row) pair's LUTs: 512 B + 64 B
+            if (combo != cur_combo) {   // this (peak, codebook row) pair's tables: 768 B
                 __syncwarp();
-                reinterpret_cast<uint4*>(sm + SM::LUT4)[lane] = g_enc4[(size_t)combo * 32 + lane];
-                if (lane < 16) s_lut1[lane] = g_enc1[(size_t)combo * 16 + lane];
+                const uint4* src = g_enc4 + (size_t)combo * (EF_LUT_B / 16);
+                for (int i = lane; i < EF_LUT_B / 16; i += 32) reinterpret_cast<uint4*>(sm + SM::LUT)[i] = src[i];
                 cur_combo = combo;
                 __syncwarp();
             }
             const uint8_t* row = P.L.sym + ch_off(P.L, c);
-            const int A0 = start & ~(ETILE - 1);
+            const int A0 = start & ~63;                   // tiles start with the window (rounded down to a lane's 64 symbols)
             const int nt = (end - A0 + ETILE - 1) / ETILE;
             const int rd_end = (end + 15) & ~15;
-            // chunk (1024-symbol) side info: tile t holds chunks EF_NG*t+dj .. +EF_NG-1, numbered from start/1024
-            uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride + (A0 / TILE - start / TILE);
+            // chunk (1024-symbol) side info, numbered from start/1024; chunk 0 starts with the window
+            uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride - start / TILE;
+            if (lane == 0) co[start / TILE] = 0;
+            // full tiles: the two absolute multiples of 1024 inside a tile are the first symbols of the same two lanes in every
+            // tile of the channel (the tile origin is a multiple of 64)
+            const int l1 = ((-A0) & (TILE - 1)) >> 6;      // 0..15
+            const bool own_b = (lane & 15) == l1;          // this lane starts a chunk (lanes l1 and l1 + 16)
+            uint32_t* co_l = co + ((A0 + 64 * l1 + (lane >> 4) * TILE) >> 10);   // its side-info slot in tile 0 (+2 per tile)
             uint8_t* out = P.stream + (size_t)c * P.slot_bytes;
             uint32_t carry = 0;
 
@@ -398,17 +456,38 @@ __global__ void __launch_bounds__(EF_WARPS * 32, EF_NG == 2 ? 4 : 5) k_encode_fa
             int ts = A0;
             for (int t = 0; t < nt; ++t, ts += ETILE) {
                 mbar_wait(&s_bar[slot], parity);
-                const uint8_t* tile = s_in + slot * ETILE + lane * (32 * EF_NG);
+                const uint8_t* tile_w = s_in + slot * ETILE;
                 const uint32_t Pold = Pbits;
-                uint32_t a_lane;
+                uint32_t a_lane, pc[4], pl[4];
                 const bool full = (ts >= start) && (ts + ETILE <= end);       // warp-uniform
-                if (full) enc_fast_tile<true, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, gmul, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
-                else enc_fast_tile<false, RM, EF_NG>(tile, lut4_saddr, s_lut1, satk, satv, gmul, ts, start, end, lane, s_ring, Pbits, carry, a_lane);
-                // chunk offsets: every (32 / EF_NG)-th lane starts one of the tile's EF_NG chunks
-                if ((lane & (32 / EF_NG - 1)) == 0) {
-                    const int k = lane / (32 / EF_NG);
-                    const int cs = ts + k * TILE;                             // absolute start of that chunk
-                    if (cs + TILE > start && cs < end) co[EF_NG * t + k] = a_lane;
+                if (full) {
+                    enc_fast_pieces<SV>(tile_w + lane * 64, lut_saddr, lane, pc, pl);
+                    enc_fast_place<true, RM>(pc, pl, lane, s_ring, Pbits, carry, a_lane);
+                    if (own_b) co_l[2 * t] = a_lane;
+                } else {
+                    // partial tile: k 16-symbol pieces per lane cover what is left of the window
+                    const int k = min(4, (end - ts + 511) >> 9);
+                    enc_fast_pieces_partial<SV>(tile_w, lut_saddr + 256, ts, start, end, k, lane, pc, pl);
+                    enc_fast_place<false, RM>(pc, pl, lane, s_ring, Pbits, carry, a_lane);
+                    // chunk offsets: the (at most two) absolute multiples of 1024 inside the tile and strictly inside the window
+                    const uint32_t kinv = k == 4 ? 64u : (k == 3 ? 86u : (k == 2 ? 128u : 256u));   // floor(pi / k) = pi * kinv >> 8 for pi < 128
+                    int cs = (ts + TILE - 1) & ~(TILE - 1);
+                    const int cs_end = min(end, ts + ETILE);
+                    if (cs <= start) cs += TILE;
+#pragma unroll
+                    for (int b = 0; b < 2; ++b, cs += TILE) {
+                        if (cs < cs_end) {
+                            const int pi = (cs - ts) >> 4;                    // piece of the tile the chunk starts with
+                            const int ol = (int)(((uint32_t)pi * kinv) >> 8), sub = pi - ol * k;
+                            if (lane == ol) {
+                                uint32_t o = a_lane;
+                                if (sub > 0) o += pl[0];
+                                if (sub > 1) o += pl[1];
+                                if (sub > 2) o += pl[2];
+                                co[cs >> 10] = o;
+                            }
+                        }
+                    }
                 }
                 // ---- flush complete 128-bit units; refill the TMA slot ----
                 __syncwarp();
