@@ -48,21 +48,6 @@ int sm_count() {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// cuTensorMapEncodeTiled through the runtime (no link against libcuda): the tensor view of a decoded buffer for k_decode_lane_t
-typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-TensorMapEncodeTiledFn tensor_map_encoder() {
-    static TensorMapEncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<TensorMapEncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
 int check_layout(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C) {
     REQUIRE(C >= 0, "C < 0");
     REQUIRE(d_sym != nullptr || C == 0, "d_sym is NULL");      // a recording without channels has no buffer
@@ -630,34 +615,6 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
 #ifndef MUA_DV_EXTRA
 #define MUA_DV_EXTRA 256      // bits a staged stream row of k_decode_var holds beyond one worst-case period
 #endif
-#ifndef MUA_DEC_TMA
-#define MUA_DEC_TMA 1
-#endif
-            // fixed row stride: full rows of the output tile leave through the TMA engine (k_decode_lane_t)
-            if (MUA_DEC_TMA && !d_off && (long long)C * P.item_chunks < (1ll << 31) && tensor_map_encoder()) {
-                DecTmaParams PT;
-                PT.D = P;
-                PT.Q = (P.item_chunks - 1) / 8;
-                PT.L = P.item_chunks - 8 * PT.Q;
-                const long long ga = ((long long)C * PT.Q + 3) / 4, gb = ((long long)C * PT.L + 31) / 32;
-                PT.groupsA = (uint32_t)ga;
-                PT.groups = (uint32_t)(ga + gb);
-                const cuuint64_t gdim[3] = {1024, (cuuint64_t)((stride + 1023) / 1024), (cuuint64_t)C};
-                const cuuint64_t gstr[2] = {1024, (cuuint64_t)stride};
-                const cuuint32_t box[3] = {128, 8, 1}, estr[3] = {1, 1, 1};
-                const CUresult r = tensor_map_encoder()(&PT.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_dec, gdim, gstr, box, estr,
-                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r == CUDA_SUCCESS) {
-                    cudaError_t e = cudaFuncSetAttribute(k_decode_lane_t<DT_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
-                    if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
-                    const long long blocks_needed = (ga + gb + DT_WARPS - 1) / DT_WARPS;
-                    const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
-                    k_decode_lane_t<DT_NB><<<grid, DT_WARPS * 32, DL_SMEM, st>>>(PT);
-                    CHECK_LAUNCH("k_decode");
-                    return MUA_OK;
-                }
-            }
             constexpr int NC = MUA_DL_NC;
             cudaError_t e = cudaFuncSetAttribute(k_decode_lane<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");

@@ -1,8 +1,6 @@
 // Stage 6: table-driven chunk-parallel decode (one lane per 1024-symbol chunk, multi-symbol LUT),
 // the device-side round-trip check, the synthetic MUA generator and the binning kernels (stage 1).
 #pragma once
-#include <cuda.h>
-
 #include "mua_common.cuh"
 
 namespace mua {
@@ -472,6 +470,10 @@ __global__ void __launch_bounds__(DF_WARPS * 32, 4) k_decode_fast(const __grid_c
 //   * the write-out (8 lanes per 128-byte row) uses per-group precomputed row pointers and store counts (for how many
 //     periods a pass stores a complete aligned 16 bytes); periods with window edges or unaligned rows are flagged
 //     warp-wide and take a general byte-store path.
+// (Round 2 tried the other way out of the tile: the decoded buffer described to the TMA engine as a 3-D tensor (byte in chunk, chunk,
+// channel), one 128 x 8 box store per eight lanes and period from a 128-byte-swizzled dense tile -- commit d9cb5c0 of this repository's
+// history, "Experiment: lane decoder with TMA tensor stores".  Bit-exact, LSU data pipe 60 -> 41 %, 90 registers instead of 120, and
+// SLOWER: 1.18 vs 1.13 ms.  The write-out is not what bounds this kernel; see profiles/r02_summary.md.)
 #ifndef MUA_DL_TICKETS
 #define MUA_DL_TICKETS 1
 #endif
@@ -822,266 +824,6 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
         g = gn;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    dec_wait_report(P);
-}
-
-// ---- lane decoder with TMA tensor stores (fixed row stride; same tables, lookup chain and stream ring as k_decode_lane) ----
-// k_decode_lane moves every decoded symbol through the LSU data pipe three times (STS into the tile, LDS.128 out of it, STG.128),
-// 12 of its ~21 shared-memory wavefronts per 512 symbols, and that pipe is what its dependent lookups wait for.  Here a full
-// 128-byte row of the tile leaves the SM through the TMA engine instead: the decoded buffer is described to the hardware as a
-// 3-D tensor (byte in chunk: 1024, chunk in channel: stride 1024 B, channel: stride = row stride -- the driver accepts a row stride
-// that is not a multiple of 1024) and ONE cp.async.bulk.tensor store per eight lanes and period writes eight 128-byte rows
-// (box 128 x 8 x 1, 128-byte swizzle: row l keeps its 16-byte piece q at position q ^ (l & 7), so the lanes' 16-byte tile stores
-// stay conflict-free with dense 128-byte rows).  No write-out registers (row pointers, store counts), no LDS.128 / STG.128.
-// Work items: per channel the chunks 1..8Q (Q = (item_chunks - 1) / 8) form Q octets of eight consecutive chunks; an octet whose
-// eight chunks are complete 1024-symbol chunks (every octet of a long window) is stored by TMA; the head chunk, the chunks after
-// the last octet and octets cut by a window end are "leftover" rows and take the generic row path (eight lanes per row, 16 / 8 / 4 /
-// 1-byte stores by alignment, predicated on the window).  Groups of type A are four octets, groups of type B 32 leftover chunks.
-#ifndef MUA_DT_WARPS
-#define MUA_DT_WARPS 14
-#endif
-#ifndef MUA_DT_NB
-#define MUA_DT_NB 2
-#endif
-constexpr int DT_WARPS = MUA_DT_WARPS;
-constexpr int DT_NB = MUA_DT_NB;                  // output tiles per warp (2: a tile is refilled while the TMA engine still reads the other)
-constexpr int DT_TILE_B = 32 * 128;               // dense 128-byte rows, swizzled
-constexpr int DT_UNIT_B = (DT_NB * DT_TILE_B + 32 * DL_ROW_B + 1023) / 1024 * 1024;   // per warp: tiles (1024-byte aligned), stream ring
-
-struct DecTmaParams {
-    DecParams D;
-    int32_t Q, L;                                 // octets and leftover chunks per channel: item_chunks = 8 Q + L
-    uint32_t groupsA, groups;                     // type-A groups (four octets each), all groups
-    alignas(64) CUtensorMap tmap;                 // uint8 [C][stride / 1024][1024], box 128 x 8 x 1, 128-byte swizzle
-};
-
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int x, int y, int z) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src_smem), "r"(x),
-                 "r"(y), "r"(z)
-                 : "memory");
-}
-
-template <int NB>
-__global__ void __launch_bounds__(DT_WARPS * 32, 1) k_decode_lane_t(const __grid_constant__ DecTmaParams PT) {
-    extern __shared__ __align__(1024) uint8_t dsm[];
-    const DecParams& P = PT.D;
-    const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
-    const int K = T->K;
-    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->W != 8 || K > DL_MAX_ROWS || T->S > 8 || P.off != nullptr) {
-        if (threadIdx.x == 0) dec_flag(P.status, MUA_DEC_BAD_TABLE);   // host view does not match the table block
-        return;
-    }
-    const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- shared-memory layout: rank -> symbol maps, per-warp units (tiles + ring) below and above the tables (32 KB aligned) ----
-    const uint32_t map_a = smem_u32(dsm);                         // uint2 [8]: idx[p][0..7]; word 16: ticket
-    const uint32_t base_a = (map_a + 128 + 1023) & ~1023u;
-    const uint32_t tab_a = (map_a + 128 + (DL_TAB_B - 1)) & ~(uint32_t)(DL_TAB_B - 1);
-    const uint32_t hi_a = tab_a + K * DL_TAB_B;
-    const uint32_t end_a = map_a + DL_SMEM;
-    const int n_low = tab_a > base_a ? (int)((tab_a - base_a) / DT_UNIT_B) : 0;
-    const int n_high = hi_a <= end_a ? (int)((end_a - hi_a) / DT_UNIT_B) : 0;
-    const int nw = min(DT_WARPS, n_low + n_high);                 // warps that have their buffers
-    {
-        uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm + (tab_a - map_a));
-        const int nword = K * 256 * 32;
-        for (int i = threadIdx.x; i < nword; i += blockDim.x) {
-            const int e = i >> 5, k = e >> 8, idx = e & 255;
-            const uint32_t v = g_lut[k * 256 + idx];
-            const uint32_t sel = (v & 0xFu) | ((v >> 4) & 0xF0u) | ((v >> 8) & 0xF00u) | ((v >> 12) & 0xF000u);
-            s_lut[(k * 256 + (int)(__brev((uint32_t)idx) >> 24)) * 32 + (i & 31)] = sel | (v & 0xF0000000u);
-        }
-        if (threadIdx.x < 16) {
-            const int p = threadIdx.x >> 1, h = threadIdx.x & 1;
-            uint32_t m = 0;
-            if (p < T->S)
-                for (int r = 0; r < 4; ++r) m |= (uint32_t)T->idx[p][4 * h + r] << (8 * r);
-            reinterpret_cast<uint32_t*>(dsm)[threadIdx.x] = m;
-        }
-        if (threadIdx.x == 16) reinterpret_cast<uint32_t*>(dsm)[16] = (uint32_t)nw;     // next group ticket of this CTA
-    }
-    __syncthreads();
-    if (warp >= nw) return;
-    const uint32_t unit_a = warp < n_low ? base_a + warp * DT_UNIT_B : hi_a + (warp - n_low) * DT_UNIT_B;
-    const uint32_t ring_a = unit_a + NB * DT_TILE_B + lane * DL_ROW_B;
-    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(dsm + (ring_a - map_a));
-    const int col8 = lane & 7, oct0 = lane & 24;
-    const bool issuer = col8 == 0;
-    const unsigned long long lo_addr = reinterpret_cast<unsigned long long>(P.stream);
-    const unsigned long long hi_addr = lo_addr + (unsigned long long)P.C * (unsigned long long)P.slot_bytes;
-    const uint32_t Q = (uint32_t)PT.Q, L = (uint32_t)PT.L;
-    const uint32_t noct = (uint32_t)P.C * Q, nleft = (uint32_t)P.C * L;
-    const uint32_t ngroups = PT.groups;
-
-    // this lane's chunk of group g: type A = octet (g * 4 + lane / 8), chunk 1 + 8 q + lane % 8; type B = leftover chunk
-    auto load_item = [&](uint32_t g, bool& type_a) -> DecItem {
-        int c = 0, j = 0;
-        bool valid = false;
-        type_a = g < PT.groupsA;
-        if (type_a) {
-            const uint32_t o = g * 4u + (uint32_t)(lane >> 3);
-            if (o < noct) { c = (int)(o / Q); j = 1 + 8 * (int)(o - (uint32_t)c * Q) + col8; valid = true; }
-        } else if (g < ngroups) {
-            const uint32_t i = (g - PT.groupsA) * 32u + (uint32_t)lane;
-            if (i < nleft) { c = (int)(i / L); const int k = (int)(i - (uint32_t)c * L); j = k ? 8 * (int)Q + k : 0; valid = true; }
-        }
-        return dec_finish(P, dec_load_cj(P, c, j, valid), K, T->S);
-    };
-    auto ring_start = [&](const DecItem& it, DecRing& R) {
-        R.org = (reinterpret_cast<unsigned long long>(it.sbase) + (it.bp >> 3)) & ~31ull;
-        R.wp = 96;
-        if (it.rem > 0) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const unsigned long long a = R.org + 16 * k;
-                if (a >= lo_addr && a + 16 <= hi_addr) cp_async16(ring_a + 16 * k, a);
-            }
-        }
-    };
-
-    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(dsm) + 16;
-    const uint32_t gstride = gridDim.x * (uint32_t)nw;
-    uint32_t g = blockIdx.x * (uint32_t)nw + warp;
-    bool type_a;
-    DecItem cur = load_item(g, type_a);
-    DecRing R;
-    ring_start(cur, R);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    uint32_t pcount = 0;                                           // periods so far: tile = pcount % NB
-    while (g < ngroups) {
-        uint32_t gn = g + gstride;
-        bool type_an = false;
-        const uint32_t lbase = tab_a + (uint32_t)cur.en * DL_TAB_B + lane * 4;       // this lane's bank of its row's table
-        uint32_t mlo, mhi;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mlo), "=r"(mhi) : "r"(map_a + cur.pk * 8));
-        const int rem = cur.rem;
-        const unsigned long long optr_self = reinterpret_cast<unsigned long long>(cur.optr);
-        // an octet all of whose chunks are complete goes out through the TMA engine: row (chunk) y of channel z
-        const unsigned fullm = __ballot_sync(FULL, type_a && rem == TILE);
-        const bool tma_oct = ((fullm >> oct0) & 0xFFu) == 0xFFu;
-        const int ty = cur.col >> 10, tz = cur.ch;
-        const bool any_generic = __any_sync(FULL, !tma_oct && rem > 0);
-        // position of the chunk's first bit in the ring frame
-        const uint32_t boff = (uint32_t)(reinterpret_cast<unsigned long long>(cur.sbase) + (cur.bp >> 3) - R.org) * 8 + (cur.bp & 7);
-        uint32_t rp = boff >> 5, off = boff & 31, w0 = 0, w1 = 0, wn = 0;
-        int done = 0;
-        const int nper = max((__reduce_max_sync(FULL, rem) + 127) >> 7, 1);            // periods of this group
-        for (int per = 0; per < nper; ++per, ++pcount) {
-            // ---- top the ring up for the NEXT period, then wait for everything issued before that ----
-            if (rem > done + 128) {
-                const uint32_t rd32 = (done == 0 ? rp : rp - 3) * 4 & ~31u;            // read position, rounded down to 32 bytes
-                if (R.wp + 32 - rd32 <= 128) {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const unsigned long long a = R.org + R.wp + 16 * k;
-                        if (a + 16 <= hi_addr) cp_async16(ring_a + ((R.wp + 16 * k) & 127), a);
-                    }
-                    R.wp += 32;
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            // the tile of this period: the TMA store that read it NB periods ago must have finished reading
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NB - 1) : "memory");
-            __syncwarp();
-            if (done == 0) {
-                w0 = stream_rev(rowp[rp]); w1 = stream_rev(rowp[rp + 1]);
-                wn = rowp[rp + 2];                                                       // kept raw, see the refill below
-                rp += 3;
-            }
-            const uint32_t tile_a = unit_a + (pcount % NB) * DT_TILE_B;
-            const uint32_t trow_a = tile_a + lane * 128;
-            // ---- 128 symbols per lane into the output tile (piece q of row l at position q ^ (l & 7)) ----
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                uint32_t ow[4];
-                const uint32_t xr = __funnelshift_r(w0, w1, off);                        // next 32 stream bits, first one at bit 0
-                const uint32_t xl = xr << 7, xh = xr >> 25;
-                uint32_t o = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t t = __funnelshift_r(xl, xh, o);                       // window of this lookup on bits [14:7]
-                    uint32_t adr;                                                        // (t & 0x7F80) | lbase in one LOP3
-                    asm("lop3.b32 %0, %1, 0x7F80, %2, 0xEA;" : "=r"(adr) : "r"(t), "r"(lbase));
-                    const uint32_t e = lds_u32(adr);
-                    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ow[k]) : "r"(mlo), "r"(mhi), "r"(e));   // ranks -> symbols
-                    o += e >> 28;
-                }
-                off += o;
-                {   // branch-free refill (see k_decode_lane)
-                    const bool rf = off >= 32;
-                    const uint32_t nxt = rowp[rp & 31];
-                    const uint32_t w1n = stream_rev(wn);
-                    w0 = rf ? w1 : w0;
-                    w1 = rf ? w1n : w1;
-                    wn = rf ? nxt : wn;
-                    rp += rf ? 1u : 0u;
-                    off -= rf ? 32u : 0u;
-                }
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(trow_a + (uint32_t)((q ^ col8) << 4)), "r"(ow[0]), "r"(ow[1]),
-                             "r"(ow[2]), "r"(ow[3])
-                             : "memory");
-            }
-            DecItem nxt_item = cur;
-            if (per == nper - 1) {   // the ring is free: start the next group's chunks before writing this period out
-                uint32_t tk = 0;
-                if (lane == 0) tk = atomicAdd(s_ticket, 1u);
-                tk = __shfl_sync(FULL, tk, 0);
-                gn = blockIdx.x * (uint32_t)nw + (tk % (uint32_t)nw) + (tk / (uint32_t)nw) * gstride;
-                nxt_item = load_item(gn, type_an);
-            }
-            // ---- write-out ----
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' tile stores, before the TMA engine reads them
-            __syncwarp();
-            if (tma_oct) {
-                if (issuer) {
-                    tma_store_3d(&PT.tmap, trow_a, done, ty, tz);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            }
-            if (any_generic) {
-                // leftover rows: the eight lanes of an octet store one row of theirs at a time, 16 bytes each, inside the window only
-                const int left_self = min(max(rem - done, 0), 128);      // valid bytes of my row in this period
-#pragma unroll 1
-                for (int r = 0; r < 8; ++r) {
-                    const int src = oct0 + r;
-                    const int vr = __shfl_sync(FULL, left_self, src) - col8 * 16;          // valid bytes from this lane's column on
-                    const unsigned long long dptr = __shfl_sync(FULL, optr_self, src) + (unsigned long long)(done + col8 * 16);
-                    if (!tma_oct && vr > 0) {
-                        uint4 v;
-                        const uint32_t sa = tile_a + src * 128 + (uint32_t)((col8 ^ (src & 7)) << 4);
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
-                        uint8_t* d = reinterpret_cast<uint8_t*>(dptr);
-                        if (vr >= 16 && (dptr & 15) == 0) {
-                            *reinterpret_cast<uint4*>(d) = v;
-                        } else if (vr >= 16 && (dptr & 7) == 0) {
-                            reinterpret_cast<uint2*>(d)[0] = make_uint2(v.x, v.y);
-                            reinterpret_cast<uint2*>(d)[1] = make_uint2(v.z, v.w);
-                        } else if (vr >= 16 && (dptr & 3) == 0) {
-                            reinterpret_cast<uint32_t*>(d)[0] = v.x; reinterpret_cast<uint32_t*>(d)[1] = v.y;
-                            reinterpret_cast<uint32_t*>(d)[2] = v.z; reinterpret_cast<uint32_t*>(d)[3] = v.w;
-                        } else {
-                            const int nbyte = min(16, vr);
-                            for (int kk = 0; kk < nbyte; ++kk) {
-                                const uint32_t w = kk < 8 ? (kk < 4 ? v.x : v.y) : (kk < 12 ? v.z : v.w);
-                                d[kk] = (uint8_t)(w >> (8 * (kk & 3)));
-                            }
-                        }
-                    }
-                }
-            }
-            if (per == nper - 1) {
-                cur = nxt_item;
-                ring_start(cur, R);
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            }
-            done += 128;
-        }
-        g = gn;
-        type_a = type_an;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     dec_wait_report(P);
 }
 
