@@ -91,6 +91,23 @@ __device__ __forceinline__ uint32_t dv_syms(uint32_t e, uint32_t m0, uint32_t m1
     return syms;
 }
 
+// table entry of the window in the low bits of x; windows that start with the bits of the all-zero window's entry (x & zm == 0)
+// are that entry (ez) and do not load
+#ifndef MUA_DV_ZSKIP
+#define MUA_DV_ZSKIP 1
+#endif
+__device__ __forceinline__ uint32_t dv_lookup(uint32_t tab_sa, uint32_t x, uint32_t wmask, uint32_t zm, uint32_t ez) {
+    uint32_t e;
+#if MUA_DV_ZSKIP
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, %3;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+        : "=r"(e)
+        : "r"(tab_sa + ((x & wmask) << 2)), "r"(x & zm), "r"(ez));
+#else
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(tab_sa + ((x & wmask) << 2)));
+#endif
+    return e;
+}
+
 #ifndef MUA_DV_WARPS
 #define MUA_DV_WARPS 20
 #endif
@@ -191,6 +208,13 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
                 }
             }
         }
+        // The entry of the all-zero window (four symbols of rank 0 whenever their codewords fit) is the entry of EVERY window that
+        // starts with the bits it uses -- most windows of MUA counts.  Those lookups are answered from a register and their lanes
+        // take no part in the table load: fewer distinct addresses per load, fewer bank conflicts (the loads were 60 % of the kernel's
+        // shared-memory wavefronts, half of them conflicts).
+        const uint32_t tab_sa = smem_u32(tab);
+        const uint32_t ez = tab[0];
+        const uint32_t zm = (ez & 0x40000u) ? ((1u << ((ez >> 20) & 0xFu)) - 1u) : wmask;
         int done = 0;                                            // symbols already written out
         while (__any_sync(FULL, rem > 0)) {
             // ---- stage one period's stream bytes per lane (one TMA bulk copy each), from the 16-byte unit holding `bitpos` ----
@@ -235,9 +259,9 @@ __global__ void __launch_bounds__(DV_WARPS * 32, 1) k_decode_var(const __grid_co
 #pragma unroll 2
                 for (int q = 0; q < 16; ++q) {
                     const uint32_t x = __funnelshift_r(w0, w1, off);             // next 32 stream bits, first one at bit 0
-                    const uint32_t eA = tab[x & wmask];
+                    const uint32_t eA = dv_lookup(tab_sa, x, wmask, zm, ez);
                     const uint32_t uA = (eA >> 20) & 0xFu;
-                    const uint32_t eB = tab[(x >> uA) & wmask];
+                    const uint32_t eB = dv_lookup(tab_sa, x >> uA, wmask, zm, ez);
                     uint32_t sA = dv_syms<WIDE>(eA, m0, m1, m2, m3), sB = dv_syms<WIDE>(eB, m0, m1, m2, m3);
                     uint32_t used = uA + ((eB >> 20) & 0xFu);
                     const bool esc = ((eA & eB) & 0x40000u) == 0u && q * 8 < rem;   // count field [18:16] == 4 <=> bit 18

@@ -9,7 +9,7 @@ tail -4 gpurun_out/${TAG}_pytest.log
 python tools/sweep_bench.py > gpurun_out/${TAG}_sweep.log 2>&1 && cp gpurun_out/sweep.json gpurun_out/${TAG}_sweep.json
 python tools/show_sweep.py gpurun_out/${TAG}_sweep.json | tail -14
 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-seconds 0.5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-python - <<'PY'
+python - $TAG <<'PY'
 import json,sys
 d=json.load(open("gpurun_out/%s_bench.json" % (sys.argv[1] if len(sys.argv)>1 else "r02c")))
 print({k: d["stages"][k] for k in ("calibrate_ms","encode_ms","decode_ms","encode_frac","decode_frac")}, d["ms_per_step"], d["lossless"])
