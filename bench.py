@@ -4,14 +4,15 @@
 One "step" = one pass of the hot path (calibrate -> Huffman encode -> chunk-parallel decode) over
 this rank's shard of the cfg5 synthetic stream (BASELINE.json configs[4]: 1M channels x 1 h @ 50 ms
 sharded over 8 GPUs = 125 000 channels x 72 000 bins per GPU, S=3, H=64, codebook 0/10/11);
-weak scaling: every rank processes its own 125k-channel shard, only the per-channel report
-(bits, symbols, SCLV index, peak) is gathered with NCCL inside the step.
+weak scaling: every rank processes its own 125k-channel shard; the per-channel report (bits, symbols,
+SCLV index, peak) reaches every rank inside the step through peer-memory stores of the encoder
+(--report p2p, default) or one NCCL all-gather (--report nccl).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
   torchrun --nproc-per-node N bench.py --gpus N ...          (N > 1)
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU path instead (literal
-port in oracle/ref_port.py on all host cores; the Python reference itself cannot travel to the box)."""
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU path instead: the
+UNMODIFIED reference loop staged under oracle/_ref (oracle/make_ref.py), one process per host core."""
 import argparse
 import json
 import os
