@@ -33,11 +33,23 @@ def test_decode_writes_only_the_window(S, lens, sclv_tables):
     slot = cb.worst_case_slot_bytes(T)
     nchunk = (T + 1023) // 1024
     big = torch.full((C + 1, slot), 0xA5, dtype=torch.uint8, device=DEV)              # one guard slot behind the last
-    es = P.EncodedStreams(stream=big[:C], chunk_off=torch.zeros((C, nchunk), dtype=torch.int32, device=DEV),
-                          total_bits=torch.zeros(C, dtype=torch.int64, device=DEV),
-                          overflow=torch.zeros(1, dtype=torch.int32, device=DEV), slot_bytes=slot, chunk_stride=nchunk)
+    # side info inside a guarded buffer: one guard row above and below, one guard column left and right of every row
+    SENT, cs = 0x7BADBEEF, nchunk + 2
+    co_flat = torch.full(((C + 2) * cs,), SENT, dtype=torch.int32, device=DEV)
+    co = torch.as_strided(co_flat, (C, nchunk), (cs, 1), storage_offset=cs + 1)
+    tb_flat = torch.full((C + 2,), -7, dtype=torch.int64, device=DEV)
+    es = P.EncodedStreams(stream=big[:C], chunk_off=co, total_bits=tb_flat[1:C + 1],
+                          overflow=torch.zeros(1, dtype=torch.int32, device=DEV), slot_bytes=slot, chunk_stride=cs)
     P.encode(rec, cb, st, en, pk, ec, out=es)
     assert int(es.overflow.item()) == 0 and bool((big[C] == 0xA5).all())
+    assert int(tb_flat[0]) == -7 and int(tb_flat[C + 1]) == -7
+    coh = co_flat.cpu().numpy().reshape(C + 2, cs)
+    stc0, enc0 = st.cpu().numpy(), en.cpu().numpy()
+    nch = np.where(enc0 > stc0, (enc0 + 1023) // 1024 - stc0 // 1024, 0)              # chunks of every channel's window
+    written = np.zeros((C + 2, cs), dtype=bool)
+    written[1:C + 1, 1:nchunk + 1] = np.arange(nchunk)[None, :] < nch[:, None]
+    assert (coh[~written] == SENT).all(), "encoder wrote side info outside the window's chunks"
+    assert (coh[written] != SENT).all()
     used = ((es.total_bits + 127) // 128 * 16).cpu().numpy()
     streams = big[:C].cpu().numpy()
     for c in (0, C // 2, C - 1):
