@@ -603,7 +603,15 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     // chunks per channel that can be non-empty: ceil(max_end / CHUNK) when the caller bounds the window end
     P.item_chunks = chunk_stride;
     if (max_end > 0 && (max_end + TILE - 1) / TILE < chunk_stride) P.item_chunks = (max_end + TILE - 1) / TILE;
-    const long long groups = ((long long)C * P.item_chunks + 31) / 32;
+#ifndef MUA_DEC_BY_CHUNK_MAX
+#define MUA_DEC_BY_CHUNK_MAX 4       // rows of at most this many chunks are decoded chunk-major (see dec_item)
+#endif
+    // (lane decoder only: 100k x 2 400 decodes in 57 instead of 68 us; the general decoder, whose stages are paced by the warp's
+    // slowest lane either way, got slower with it: S=5 157 -> 181 us)
+    P.by_chunk = h.nsym == 4 && h.Lmax <= 2 && h.K <= DL_MAX_ROWS && h.S <= 8 && h.W == 8 && P.item_chunks >= 2 &&
+                 P.item_chunks <= MUA_DEC_BY_CHUNK_MAX;
+    const long long nitems = P.by_chunk ? (long long)((C + 31) / 32) * 32 * P.item_chunks : (long long)C * P.item_chunks;
+    const long long groups = (nitems + 31) / 32;
     const int lut_bytes = ((h.S * h.K) << h.W) * 4;
     const bool smem_lut = lut_bytes <= 32 * 1024;
     if (h.nsym == 4 && h.Lmax <= 2) {
@@ -618,7 +626,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
             constexpr int NC = MUA_DL_NC;
             cudaError_t e = cudaFuncSetAttribute(k_decode_lane<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
-            const long long lgroups = ((long long)C * P.item_chunks + 32 * NC - 1) / (32 * NC);
+            const long long lgroups = (nitems + 32 * NC - 1) / (32 * NC);
             const long long blocks_needed = (lgroups + DL_WARPS / NC - 1) / (DL_WARPS / NC);
             const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
             k_decode_lane<NC><<<grid, DL_WARPS / NC * 32, DL_SMEM, st>>>(P);
