@@ -52,7 +52,7 @@ SIGNATURES = {
     "mua_bit_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mua_elim_scores": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mua_encode": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
-                             _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
+                             _vp, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mua_pack_streams": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _i64, _vp]),
     "mua_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), _vp]),
     "mua_peer_open": (C.c_int, [_vp, C.POINTER(_vp)]),
@@ -60,7 +60,7 @@ SIGNATURES = {
     "mua_peer_free": (C.c_int, [_vp]),
     "mua_report_signal": (C.c_int, [_vp, _i32, _vp]),
     "mua_report_wait": (C.c_int, [_vp, _i32, _vp]),
-    "mua_decode": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+    "mua_decode": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                              _i32, _vp, _vp, _vp, _i32, _vp]),
     "mua_verify": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mua_online_histogram": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),

@@ -468,13 +468,15 @@ int mua_report_wait(const mua_report_sink* h_sink, int32_t step, void* stream) {
 int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C, int32_t S,
                const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak, const uint8_t* d_enc, const void* d_tables,
                int32_t K, int32_t Lmax, uint8_t* d_stream, int64_t slot_bytes, uint32_t* d_chunk_off, int32_t chunk_stride,
-               int64_t* d_total_bits, int32_t* d_overflow, const mua_report_sink* h_sink, void* stream) {
+               uint32_t* d_sub_off, int32_t sub_stride, int64_t* d_total_bits, int32_t* d_overflow, const mua_report_sink* h_sink,
+               void* stream) {
     int rc = check_layout(d_sym, d_off, d_len, stride, T, C);
     if (rc) return rc;
     if (C == 0) return MUA_OK;                                  // nothing to encode: per-channel arrays may be empty (NULL)
     REQUIRE(d_start && d_end && d_peak && d_enc && d_tables && d_stream && d_chunk_off && d_total_bits && d_overflow, "NULL argument");
     REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
     REQUIRE(chunk_stride >= (T + TILE - 1) / TILE && chunk_stride >= 1, "chunk_stride < ceil(T/%d)", TILE);
+    REQUIRE(!d_sub_off || sub_stride >= 8 * ((T + TILE - 1) / TILE), "sub_stride < 8 * ceil(T/%d)", TILE);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 0) return MUA_OK;
     REQUIRE(S >= 2 && S <= MUA_MAX_S && K >= 1 && K <= MUA_MAX_K && Lmax >= 1 && Lmax <= 9, "bad S/K/Lmax");
@@ -485,6 +487,7 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     P.S = S; P.start = d_start; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
     P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax;
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
+    P.sub_off = d_sub_off; P.sub_stride = sub_stride;
     P.total_bits = d_total_bits; P.overflow = d_overflow;
     P.n_peers = 0; P.row0 = 0; P.signal_step = 0; P.rank = 0;
     for (int i = 0; i < MUA_MAX_PEERS; ++i) { P.rep[i] = nullptr; P.flags[i] = nullptr; }
@@ -573,7 +576,8 @@ int mua_pack_streams(const uint8_t* d_stream, int64_t slot_bytes, const int64_t*
     return MUA_OK;
 }
 
-int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off, int32_t chunk_stride, const int64_t* d_off,
+int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off, int32_t chunk_stride,
+               const uint32_t* d_sub_off, int32_t sub_stride, const int64_t* d_off,
                int64_t stride, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
                const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end, uint8_t* d_dec,
                int32_t* d_status, const mua_report_sink* h_wait_sink, int32_t wait_step, void* stream) {
@@ -593,6 +597,7 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
     P.stream = d_stream; P.slot_bytes = slot_bytes; P.chunk_off = d_chunk_off; P.chunk_stride = chunk_stride;
     P.off = d_off; P.stride = stride; P.C = C; P.S = S; P.start = d_start; P.end = d_end; P.peak = d_peak; P.enc = d_enc;
     P.tab = reinterpret_cast<const uint8_t*>(d_tables); P.K = K; P.Lmax = Lmax; P.dec = d_dec; P.status = d_status;
+    P.sub_off = d_sub_off; P.sub_stride = sub_stride;
     P.wait_flags = nullptr; P.wait_n = 0; P.wait_step = 0;
     if (h_wait_sink && h_wait_sink->n_peers > 0 && wait_step > 0) {
         int rcs = check_sink(h_wait_sink);
@@ -623,6 +628,25 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
 #ifndef MUA_DV_EXTRA
 #define MUA_DV_EXTRA 256      // bits a staged stream row of k_decode_var holds beyond one worst-case period
 #endif
+#ifndef MUA_DEC_SUB
+#define MUA_DEC_SUB 1
+#endif
+#ifndef MUA_DEC_SUB_MIN_CHUNKS
+#define MUA_DEC_SUB_MIN_CHUNKS 8     // shorter windows leave most of a 32-sub-chunk group idle: lane decoder
+#endif
+            // with the encoder's 128-symbol side info (codebooks of the fast encoder's class, fixed row stride, long windows): a lane per
+            // sub-chunk, 32 consecutive sub-chunks per warp (k_decode_sub)
+            const long long sgroups = (long long)C * ((8 * P.item_chunks + 31) / 32);
+            if (MUA_DEC_SUB && d_sub_off && !d_off && h.S <= 3 && P.item_chunks >= MUA_DEC_SUB_MIN_CHUNKS && sgroups < (1ll << 31)) {
+                REQUIRE(sub_stride >= 8 * P.item_chunks, "sub_stride < 8 * chunks per channel");
+                cudaError_t e = cudaFuncSetAttribute(k_decode_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
+                if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+                const long long blocks_needed = (sgroups + DS_WARPS - 1) / DS_WARPS;
+                const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
+                k_decode_sub<<<grid, DS_WARPS * 32, DL_SMEM, st>>>(P);
+                CHECK_LAUNCH("k_decode");
+                return MUA_OK;
+            }
             constexpr int NC = MUA_DL_NC;
             cudaError_t e = cudaFuncSetAttribute(k_decode_lane<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");

@@ -10,6 +10,8 @@ struct DecParams {
     int64_t slot_bytes;
     const uint32_t* chunk_off;
     int32_t chunk_stride;
+    const uint32_t* sub_off;    // NULL, or the encoder's 128-symbol sub-chunk offsets (k_decode_sub)
+    int32_t sub_stride;
     int32_t item_chunks;        // chunks per channel that can be non-empty (<= chunk_stride)
     int32_t by_chunk;           // item order, see dec_item
     const int64_t* off;
@@ -871,6 +873,266 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
             done += 128;
         }
         g = gn;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    dec_wait_report(P);
+}
+
+// ---- sub-chunk decoder (the chosen system's codebook class, fixed row stride, the encoder's 128-symbol side info) ----
+// k_decode_lane gives every lane a 1024-symbol chunk, so a warp writes 32 rows of 128 bytes that lie 1 KB apart in every pass, and
+// its per-lane stream ring and output row limit an SM to 14 warps of dependent lookup chains.  With a bit offset for every
+// 128-symbol sub-chunk (uint32: +3.1 % of the symbol bytes) a lane decodes ONE sub-chunk and a warp 32
+// consecutive ones of a channel:
+//   * the warp's output of a pass is 4 KB of consecutive symbols, written with fully coalesced 16-byte stores from a dense,
+//     128-byte-swizzled tile (piece q of row l at position q ^ (l & 7): conflict-free for the lanes' stores and for the write-out);
+//   * the 32 lanes' stream bytes are consecutive too (<= 1 KB + slack): the warp copies them with cp.async (16 bytes per lane and
+//     round) into one of two staging buffers, one group ahead; no per-lane ring, no top-ups, no refill bookkeeping beyond a pointer;
+//   * per-warp shared memory drops to 7 KB and the state of a lane to a handful of registers: 24 warps (768 chains) per SM.
+// Same lane-private-bank tables, rank -> symbol PRMT and lookup chain as k_decode_lane.  Groups never span channels (a channel's
+// sub-chunks are padded to a multiple of 32); the side info of the next two groups and the stream of the next group are requested
+// while the current group is decoded.  Partial sub-chunks (window start / end inside) and rows that are not 16-byte aligned take
+// a per-row path with predicated, alignment-dependent stores.
+#ifndef MUA_DS_WARPS
+#define MUA_DS_WARPS 26
+#endif
+constexpr int DS_WARPS = MUA_DS_WARPS;
+constexpr int DS_STR_B = 1536;                     // staged stream bytes per group: 32 sub-chunks of <= 32 bytes + alignment + look-ahead
+constexpr int DS_TILE_B = 32 * 128;
+constexpr int DS_UNIT_B = DS_TILE_B + 2 * DS_STR_B;   // per warp: tile (1024-byte aligned), two stream buffers
+static_assert(DS_UNIT_B % 1024 == 0, "units keep the tiles 1024-byte aligned");
+
+struct DsRaw {               // the loads of one lane's sub-chunk bookkeeping, nothing derived yet
+    int c, mrel, valid;
+    int start, end, pk, en;
+    uint32_t sub;
+};
+struct DsItem {
+    int rem;                 // symbols of this lane's sub-chunk (0: idle)
+    uint32_t bitoff;         // bit offset of its first symbol in the channel's stream
+    uint8_t* optr;           // where its first symbol goes
+    const uint8_t* sbase;    // the channel's slot
+    int pk, en;
+};
+
+__device__ __forceinline__ DsRaw ds_load(const DecParams& P, uint32_t g, uint32_t ngroups, uint32_t gpc, int lane) {
+    DsRaw r;
+    r.valid = g < ngroups;
+    const uint32_t gg = r.valid ? g : 0u;
+    r.c = (int)(gg / gpc);
+    r.mrel = (int)(gg - (uint32_t)r.c * gpc) * 32 + lane;
+    r.start = ldg_s32(P.start + r.c);
+    r.end = ldg_s32(P.end + r.c);
+    r.pk = ldg_u8(P.peak + r.c);
+    r.en = ldg_u8(P.enc + r.c);
+    r.sub = ldg_u32(P.sub_off + (size_t)r.c * P.sub_stride + r.mrel);
+    return r;
+}
+
+__device__ __forceinline__ DsItem ds_finish(const DecParams& P, DsRaw r, int K, int S) {
+    asm volatile("" : "+r"(r.start), "+r"(r.end), "+r"(r.pk), "+r"(r.en), "+r"(r.sub));
+    DsItem it;
+    it.rem = 0; it.bitoff = 0; it.optr = P.dec; it.sbase = P.stream; it.pk = 0; it.en = 0;
+    if (r.valid && r.end > r.start && r.start >= 0) {
+        const int mabs = 8 * (r.start >> 10) + r.mrel;                 // absolute sub-chunk index
+        const int a = max(r.start, mabs << 7), b = min(r.end, (mabs << 7) + 128);
+        if (b > a) {
+            const uint32_t bo = r.sub;
+            if (r.pk >= S || r.en >= K) {
+                dec_flag(P.status, MUA_DEC_BAD_TABLE);
+            } else if ((long long)(bo >> 3) >= P.slot_bytes) {
+                dec_flag(P.status, MUA_DEC_BAD_OFFSET);
+            } else {
+                it.rem = b - a;
+                it.bitoff = bo;
+                it.sbase = P.stream + (size_t)r.c * P.slot_bytes;
+                it.optr = P.dec + (long long)r.c * P.stride + a;
+                it.pk = r.pk;
+                it.en = r.en;
+            }
+        }
+    }
+    return it;
+}
+
+__global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_constant__ DecParams P) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
+    const int K = T->K;
+    if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->W != 8 || K > DL_MAX_ROWS || T->S > 8 || P.off != nullptr ||
+        P.sub_off == nullptr) {
+        if (threadIdx.x == 0) dec_flag(P.status, MUA_DEC_BAD_TABLE);   // host view does not match the table block
+        return;
+    }
+    const uint32_t* g_lut = reinterpret_cast<const uint32_t*>(P.tab + T->dec_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- shared-memory layout: rank -> symbol maps + ticket, per-warp units below and above the tables (32 KB aligned) ----
+    const uint32_t map_a = smem_u32(dsm);                         // uint2 [8]: idx[p][0..7]; word 16: ticket
+    const uint32_t base_a = (map_a + 128 + 1023) & ~1023u;
+    const uint32_t tab_a = (map_a + 128 + (DL_TAB_B - 1)) & ~(uint32_t)(DL_TAB_B - 1);
+    const uint32_t hi_a = tab_a + K * DL_TAB_B;
+    const uint32_t end_a = map_a + DL_SMEM;
+    const int n_low = tab_a > base_a ? (int)((tab_a - base_a) / DS_UNIT_B) : 0;
+    const int n_high = hi_a <= end_a ? (int)((end_a - hi_a) / DS_UNIT_B) : 0;
+    const int nw = min((int)(blockDim.x >> 5), n_low + n_high);  // warps that have their buffers
+    {
+        uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm + (tab_a - map_a));
+        const int nword = K * 256 * 32;
+        for (int i = threadIdx.x; i < nword; i += blockDim.x) {
+            const int e = i >> 5, k = e >> 8, idx = e & 255;
+            const uint32_t v = g_lut[k * 256 + idx];
+            const uint32_t sel = (v & 0xFu) | ((v >> 4) & 0xF0u) | ((v >> 8) & 0xF00u) | ((v >> 12) & 0xF000u);
+            s_lut[(k * 256 + (int)(__brev((uint32_t)idx) >> 24)) * 32 + (i & 31)] = sel | (v & 0xF0000000u);
+        }
+        if (threadIdx.x < 16) {
+            const int p = threadIdx.x >> 1, h = threadIdx.x & 1;
+            uint32_t m = 0;
+            if (p < T->S)
+                for (int r = 0; r < 4; ++r) m |= (uint32_t)T->idx[p][4 * h + r] << (8 * r);
+            reinterpret_cast<uint32_t*>(dsm)[threadIdx.x] = m;
+        }
+        if (threadIdx.x == 16) reinterpret_cast<uint32_t*>(dsm)[16] = (uint32_t)(3 * nw);   // next group ticket of this CTA
+    }
+    __syncthreads();
+    if (warp >= nw) return;
+    const uint32_t unit_a = warp < n_low ? base_a + warp * DS_UNIT_B : hi_a + (warp - n_low) * DS_UNIT_B;
+    const uint32_t tile_a = unit_a;
+    const uint32_t str_a = unit_a + DS_TILE_B;                    // two buffers of DS_STR_B bytes
+    const uint32_t* s_str = reinterpret_cast<const uint32_t*>(dsm + (str_a - map_a));
+    const int col8 = lane & 7, row4 = lane >> 3;
+    const uint32_t gpc = (uint32_t)((8 * P.item_chunks + 31) / 32);   // groups per channel
+    const uint32_t ngroups = (uint32_t)P.C * gpc;
+    const uint32_t slot_bytes = (uint32_t)P.slot_bytes;
+    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(dsm) + 16;
+    const uint32_t gstride = gridDim.x * (uint32_t)nw;
+
+    // group order: the static schedule for the first three rounds (g0 + k * gstride), tickets after that
+    auto ticket_group = [&]() -> uint32_t {
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(s_ticket, 1u);
+        tk = __shfl_sync(FULL, tk, 0);
+        return blockIdx.x * (uint32_t)nw + (tk % (uint32_t)nw) + (tk / (uint32_t)nw) * gstride;
+    };
+    // request a group's stream bytes (the 16-byte units from the first lane's first bit to the last lane's last possible word)
+    auto stage = [&](const DsItem& it, int buf, uint32_t& lo_out) {
+        const uint32_t by = it.bitoff >> 3;
+        const uint32_t lo = __reduce_min_sync(FULL, it.rem > 0 ? (by & ~15u) : 0xFFFFFFFFu);
+        const uint32_t hi = __reduce_max_sync(FULL, it.rem > 0 ? ((by + 48u + 15u) & ~15u) : 0u);
+        lo_out = lo;
+        if (hi > lo) {                                            // some lane is active (all of one channel: same slot)
+            const uint8_t* sb = reinterpret_cast<const uint8_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(it.sbase),
+                                                                             __ffs(__ballot_sync(FULL, it.rem > 0)) - 1));
+            const uint32_t span = min(hi - lo, (uint32_t)DS_STR_B);
+            for (uint32_t o = lane * 16u; o < span; o += 512u)
+                if (lo + o + 16u <= slot_bytes) cp_async16(str_a + buf * DS_STR_B + o, reinterpret_cast<unsigned long long>(sb) + lo + o);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    uint32_t g0 = blockIdx.x * (uint32_t)nw + warp, g1 = g0 + gstride, g2 = g1 + gstride;
+    DsItem cur = ds_finish(P, ds_load(P, g0, ngroups, gpc, lane), K, T->S);
+    DsItem nxt = ds_finish(P, ds_load(P, g1, ngroups, gpc, lane), K, T->S);
+    DsRaw raw = ds_load(P, g2, ngroups, gpc, lane);
+    uint32_t lo_cur, lo_nxt;
+    int buf = 0;
+    stage(cur, 0, lo_cur);
+    stage(nxt, 1, lo_nxt);
+    while (g0 < ngroups) {
+        // ---- this group's lane state ----
+        const uint32_t lbase = tab_a + (uint32_t)cur.en * DL_TAB_B + lane * 4;       // this lane's bank of its row's table
+        uint32_t mlo, mhi;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mlo), "=r"(mhi) : "r"(map_a + cur.pk * 8));
+        const int rem = cur.rem;
+        const unsigned long long optr_self = reinterpret_cast<unsigned long long>(cur.optr);
+        const uint32_t* sp = s_str + buf * (DS_STR_B / 4);
+        uint32_t rp = rem > 0 ? (cur.bitoff >> 5) - (lo_cur >> 2) : 0u;
+        uint32_t off = rem > 0 ? (cur.bitoff & 31u) : 0u;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // this group's stream has landed (the next group's may be in flight)
+        __syncwarp();
+        uint32_t w0 = stream_rev(sp[rp]), w1 = stream_rev(sp[rp + 1]), wn = sp[rp + 2];
+        rp += 3;
+        const uint32_t trow_a = tile_a + lane * 128;
+        // ---- 128 symbols per lane into the tile ----
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t ow[4];
+            const uint32_t xr = __funnelshift_r(w0, w1, off);                        // next 32 stream bits, first one at bit 0
+            const uint32_t xl = xr << 7, xh = xr >> 25;
+            uint32_t o = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t t = __funnelshift_r(xl, xh, o);                       // window of this lookup on bits [14:7]
+                uint32_t adr;                                                        // (t & 0x7F80) | lbase in one LOP3
+                asm("lop3.b32 %0, %1, 0x7F80, %2, 0xEA;" : "=r"(adr) : "r"(t), "r"(lbase));
+                const uint32_t e = lds_u32(adr);
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ow[k]) : "r"(mlo), "r"(mhi), "r"(e));   // ranks -> symbols
+                o += e >> 28;
+            }
+            off += o;
+            {   // branch-free refill: the word after next is read every time and kept raw
+                const bool rf = off >= 32;
+                const uint32_t nx = sp[rp];
+                const uint32_t w1n = stream_rev(wn);
+                w0 = rf ? w1 : w0;
+                w1 = rf ? w1n : w1;
+                wn = rf ? nx : wn;
+                rp += rf ? 1u : 0u;
+                off -= rf ? 32u : 0u;
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(trow_a + (uint32_t)((q ^ col8) << 4)), "r"(ow[0]), "r"(ow[1]),
+                         "r"(ow[2]), "r"(ow[3])
+                         : "memory");
+        }
+        // ---- the groups after: finish the bookkeeping loaded a pass ago, request its stream, load the next bookkeeping ----
+        const uint32_t g3 = ticket_group();
+        DsItem nn = ds_finish(P, raw, K, T->S);
+        raw = ds_load(P, g3, ngroups, gpc, lane);
+        __syncwarp();                                             // every lane is done with this group's stream buffer and has stored its row
+        uint32_t lo_nn;
+        stage(nn, buf, lo_nn);                                    // (into the buffer just read)
+        // ---- write-out ----
+        if (__all_sync(FULL, rem == 128)) {
+            // 32 complete sub-chunks of one channel: 4 KB of consecutive symbols
+            uint8_t* d0 = reinterpret_cast<uint8_t*>(__shfl_sync(FULL, optr_self, 0));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + row4;
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(tile_a + r * 128 + (uint32_t)((col8 ^ (r & 7)) << 4)));
+                *reinterpret_cast<uint4*>(d0 + r * 128 + col8 * 16) = v;
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + row4;
+                const int vr = __shfl_sync(FULL, rem, r) - col8 * 16;                  // valid bytes from this lane's column on
+                const unsigned long long dptr = __shfl_sync(FULL, optr_self, r) + (unsigned long long)(col8 * 16);
+                if (vr > 0) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(tile_a + r * 128 + (uint32_t)((col8 ^ (r & 7)) << 4)));
+                    uint8_t* d = reinterpret_cast<uint8_t*>(dptr);
+                    if (vr >= 16 && (dptr & 15) == 0) {
+                        *reinterpret_cast<uint4*>(d) = v;
+                    } else if (vr >= 16 && (dptr & 7) == 0) {
+                        reinterpret_cast<uint2*>(d)[0] = make_uint2(v.x, v.y);
+                        reinterpret_cast<uint2*>(d)[1] = make_uint2(v.z, v.w);
+                    } else if (vr >= 16 && (dptr & 3) == 0) {
+                        reinterpret_cast<uint32_t*>(d)[0] = v.x; reinterpret_cast<uint32_t*>(d)[1] = v.y;
+                        reinterpret_cast<uint32_t*>(d)[2] = v.z; reinterpret_cast<uint32_t*>(d)[3] = v.w;
+                    } else {
+                        const int nbyte = min(16, vr);
+                        for (int kk = 0; kk < nbyte; ++kk) {
+                            const uint32_t w = kk < 8 ? (kk < 4 ? v.x : v.y) : (kk < 12 ? v.z : v.w);
+                            d[kk] = (uint8_t)(w >> (8 * (kk & 3)));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();                                             // the tile is free
+        cur = nxt; lo_cur = lo_nxt;
+        nxt = nn; lo_nxt = lo_nn;
+        buf ^= 1;
+        g0 = g1; g1 = g2; g2 = g3;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     dec_wait_report(P);

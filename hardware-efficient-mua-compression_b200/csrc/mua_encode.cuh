@@ -29,6 +29,8 @@ struct EncParams {
     int64_t slot_bytes;
     uint32_t* chunk_off;
     int32_t chunk_stride;
+    uint32_t* sub_off;    // NULL, or uint32 [C][sub_stride]: bit offset of every 128-symbol sub-chunk (fast encoder)
+    int32_t sub_stride;
     int64_t* total_bits;
     int32_t* overflow;
     // multi-GPU report sink (mua_report_sink): row (row0 + c) of every peer's int32 [C_total][4] report buffer
@@ -438,6 +440,12 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
             const int l1 = ((-A0) & (TILE - 1)) >> 6;      // 0..15
             const bool own_b = (lane & 15) == l1;          // this lane starts a chunk (lanes l1 and l1 + 16)
             uint32_t* co_l = co + ((A0 + 64 * l1 + (lane >> 4) * TILE) >> 10);   // its side-info slot in tile 0 (+2 per tile)
+            // 128-symbol sub-chunk side info (for the sub-chunk decoder): entry 8 j + i = bit offset of sub-chunk i of chunk j; in a
+            // full tile every second lane starts a sub-chunk
+            uint32_t* so = P.sub_off ? P.sub_off + (size_t)c * P.sub_stride - 8 * (start / TILE) : nullptr;
+            if (so && lane == 0) so[start >> 7] = 0;                             // the sub-chunk that holds the window start
+            const bool own_s = so && (((A0 >> 6) + lane) & 1) == 0;
+            uint32_t* so_l = so + ((A0 + 64 * lane) >> 7);                       // its slot in tile 0 (+16 per tile)
             uint8_t* out = P.stream + (size_t)c * P.slot_bytes;
             uint32_t carry = 0;
 
@@ -464,6 +472,7 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
                     enc_fast_pieces<SV>(tile_w + lane * 64, lut_saddr, lane, pc, pl);
                     enc_fast_place<true, RM>(pc, pl, lane, s_ring, Pbits, carry, a_lane);
                     if (own_b) co_l[2 * t] = a_lane;
+                    if (own_s) so_l[16 * t] = a_lane;
                 } else {
                     // partial tile: k 16-symbol pieces per lane cover what is left of the window
                     const int k = min(4, (end - ts + 511) >> 9);
@@ -486,6 +495,16 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
                                 if (sub > 2) o += pl[2];
                                 co[cs >> 10] = o;
                             }
+                        }
+                    }
+                    if (so) {
+                        // sub-chunk starts among this lane's pieces: at most one (8 pieces apart, k <= 4 pieces per lane)
+                        uint32_t o = a_lane;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int p = ts + 16 * (k * lane + i);           // absolute bin of the piece's first symbol
+                            if (i < k && (p & 127) == 0 && p > start && p < end) so[p >> 7] = o;
+                            o += pl[i];
                         }
                     }
                 }

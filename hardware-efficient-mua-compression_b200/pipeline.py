@@ -239,6 +239,7 @@ class EncodedStreams:
     overflow: torch.Tensor      # int32 [1]
     slot_bytes: int
     chunk_stride: int
+    sub_off: torch.Tensor = None   # uint32 (stored as int32 bits) [C, 8 * chunk_stride]: 128-symbol sub-chunk offsets, or None
 
     def channel_bytes(self, c):
         """(test helper) the padded stream of channel c as a host uint8 array."""
@@ -246,8 +247,11 @@ class EncodedStreams:
         return self.stream[c, :nb].cpu().numpy()
 
 
-def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None, out: EncodedStreams = None, sink=None):
+def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None, out: EncodedStreams = None, sink=None,
+           sub_offsets: bool = True):
     """Stage 5 (mua_encode): window [start[c], end[c]) of every channel -> per-channel bitstreams.
+    sub_offsets: also allocate the 128-symbol sub-chunk side info (written for codebooks with Lmax <= 2, S <= 3; see
+    include/mua_b200.h) that lets mua_decode write consecutive symbols.
     sink: a `_lib.ReportSink` (dist.PeerReport.sink(step)): every channel's report row is also stored into all peers' buffers."""
     lib = _lib.load()
     dev = rec.device
@@ -264,11 +268,14 @@ def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None,
                              chunk_off=torch.zeros((rec.C, chunk_stride), dtype=torch.int32, device=dev),
                              total_bits=torch.zeros(rec.C, dtype=torch.int64, device=dev),
                              overflow=torch.zeros(1, dtype=torch.int32, device=dev),
-                             slot_bytes=slot_bytes, chunk_stride=chunk_stride)
+                             slot_bytes=slot_bytes, chunk_stride=chunk_stride,
+                             sub_off=torch.zeros((rec.C, 8 * chunk_stride), dtype=torch.int32, device=dev) if sub_offsets else None)
+    so = out.sub_off
     with torch.cuda.device(dev):
         _lib.check(lib.mua_encode(*rec.layout_args(), cb.S, _ptr(start), _ptr(end), _ptr(peak), _ptr(enc),
                                   _ptr(cb.d_tables), cb.K, cb.Lmax, _ptr(out.stream), out.slot_bytes,
-                                  _ptr(out.chunk_off), out.chunk_stride, _ptr(out.total_bits), _ptr(out.overflow),
+                                  _ptr(out.chunk_off), out.chunk_stride, _ptr(so) if so is not None else None,
+                                  int(so.stride(0)) if so is not None else 0, _ptr(out.total_bits), _ptr(out.overflow),
                                   C.byref(sink) if sink is not None else None, _stream()))
     return out
 
@@ -318,7 +325,9 @@ def decode(es: EncodedStreams, rec: Recording, cb: Codebook, start, end, peak, e
     peak = peak.to(torch.uint8).contiguous()
     enc = enc.to(torch.uint8).contiguous()
     with torch.cuda.device(rec.device):
-        _lib.check(lib.mua_decode(_ptr(es.stream), es.slot_bytes, _ptr(es.chunk_off), es.chunk_stride, _ptr(rec.off),
+        so = es.sub_off
+        _lib.check(lib.mua_decode(_ptr(es.stream), es.slot_bytes, _ptr(es.chunk_off), es.chunk_stride,
+                                  _ptr(so) if so is not None else None, int(so.stride(0)) if so is not None else 0, _ptr(rec.off),
                                   int(rec.stride), rec.C, cb.S, _ptr(start), _ptr(end), _ptr(peak), _ptr(enc),
                                   _ptr(cb.d_tables), cb.K, cb.Lmax, int(max_end), _ptr(out), _ptr(status),
                                   C.byref(wait_sink) if wait_sink is not None else None, int(wait_step), _stream()))

@@ -228,14 +228,19 @@ int mua_report_wait(const mua_report_sink* h_sink, int32_t step, void* stream);
  *                   (caller zeroes it)
  *   K, Lmax       : rows and longest codeword of the table block (as passed to mua_build_tables);
  *                   host-side launch configuration only, the kernels cross-check them
+ *   d_sub_off     : NULL, or uint32 [C][sub_stride], sub_stride >= 8 * chunk_stride: finer side info for the sub-chunk decoder.
+ *                   Entry 8 j + i = bit offset of the first window symbol of the 128-symbol sub-chunk i of chunk j (absolute
+ *                   bins [1024 (start/1024 + j) + 128 i, + 128); entry 8 j == d_chunk_off entry j); written for the
+ *                   sub-chunks that intersect the window, and only by the encoder of codebooks with Lmax <= 2 and S <= 3 (the
+ *                   chosen system); mua_decode uses it for exactly those codebooks and ignores it otherwise
  *   h_sink        : NULL, or the multi-GPU report sink: row (row0 + c) = {total_bits, max(end - start, 0), enc, peak}
  *                   as int32 is also stored into every peer's d_report (bit counts must fit int32: T * Lmax < 2^31) */
 int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride,
                int32_t T, int32_t C, int32_t S, const int32_t* d_start, const int32_t* d_end,
                const uint8_t* d_peak, const uint8_t* d_enc, const void* d_tables, int32_t K,
                int32_t Lmax, uint8_t* d_stream, int64_t slot_bytes, uint32_t* d_chunk_off,
-               int32_t chunk_stride, int64_t* d_total_bits, int32_t* d_overflow,
-               const mua_report_sink* h_sink, void* stream);
+               int32_t chunk_stride, uint32_t* d_sub_off, int32_t sub_stride, int64_t* d_total_bits,
+               int32_t* d_overflow, const mua_report_sink* h_sink, void* stream);
 
 /* Pack the used part of every channel's slot back to back (what a caller ships off the device or stores: slots are sized for
  * the worst case, a stream uses ceil(total_bits / 128) 16-byte units of its slot).
@@ -253,11 +258,14 @@ int mua_pack_streams(const uint8_t* d_stream, int64_t slot_bytes, const int64_t*
  * d_status: int32 [1], zeroed by the caller; MUA_DEC_BAD_OFFSET / MUA_DEC_BAD_TABLE (the larger one wins) when
  * something was not decoded -- a decode after an encode that set MUA_ENC_OVERFLOW reports MUA_DEC_BAD_OFFSET
  * for the chunks that start past the slot and garbage-free output cannot be assumed for the truncated channel.
+ * d_sub_off / sub_stride: NULL / 0, or the sub-chunk side info mua_encode wrote (same codebook class only): the decoder then
+ * works on 128-symbol sub-chunks, 32 consecutive ones per warp, and writes 4 KB of consecutive symbols per warp and pass
+ * instead of 32 rows of 128 bytes 1 KB apart (fixed row stride only, windows of at least eight chunks).
  * h_wait_sink / wait_step: NULL / 0, or the multi-GPU report sink: the decode's first block ends by polling the own flag
  * block until every rank has signalled `wait_step` (what mua_report_wait does as a separate launch), so a round-trip decode
  * that follows the encode also completes the gathered report. */
 int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_chunk_off,
-               int32_t chunk_stride, const int64_t* d_off, int64_t stride, int32_t C, int32_t S,
+               int32_t chunk_stride, const uint32_t* d_sub_off, int32_t sub_stride, const int64_t* d_off, int64_t stride, int32_t C, int32_t S,
                const int32_t* d_start, const int32_t* d_end, const uint8_t* d_peak,
                const uint8_t* d_enc, const void* d_tables, int32_t K, int32_t Lmax, int32_t max_end,
                uint8_t* d_dec, int32_t* d_status, const mua_report_sink* h_wait_sink, int32_t wait_step,

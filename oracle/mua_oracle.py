@@ -391,6 +391,30 @@ def encode_channel(x: np.ndarray, start: int, end: int, S: int, rank: np.ndarray
     return out, total, offs
 
 
+def sub_chunk_offsets(x: np.ndarray, start: int, end: int, S: int, rank: np.ndarray, lens: np.ndarray,
+                      chunk: int = CHUNK, sub: int = 128):
+    """Finer side info of the stream format (include/mua_b200.h, d_sub_off): for every `sub`-symbol sub-chunk (absolute bins
+    [m*sub, (m+1)*sub)) that intersects the window, the bit offset of its first window symbol.
+    Returns (values uint32 [n_chunks * chunk/sub], written bool [same]); entry (chunk/sub)*j + i belongs to
+    sub-chunk i of chunk j (chunks numbered from start // chunk as in encode_channel)."""
+    end = min(end, len(x))
+    xs = np.minimum(x[start:end].astype(np.int64), S - 1)
+    L = np.asarray(lens, dtype=np.int64)[np.asarray(rank, dtype=np.int64)[xs]]
+    starts = np.concatenate([[0], np.cumsum(L)])             # bit offset of window symbol k (k = len -> total)
+    nch, j0 = chunk_grid(start, end, chunk)
+    per = chunk // sub
+    vals = np.zeros(nch * per, dtype=np.uint32)
+    written = np.zeros(nch * per, dtype=bool)
+    for j in range(nch):
+        for i in range(per):
+            lo, hi = (j0 + j) * chunk + i * sub, (j0 + j) * chunk + (i + 1) * sub
+            a, b = max(start, lo), min(end, hi)
+            if b > a:
+                vals[j * per + i] = starts[a - start]
+                written[j * per + i] = True
+    return vals, written
+
+
 def build_decode_tree(codes, lens):
     """prefix-code lookup {(len, code): rank}."""
     return {(int(l), int(c)): r for r, (c, l) in enumerate(zip(codes, lens))}

@@ -45,6 +45,7 @@ int main(void) {
     void* d_tab;
     int32_t *d_cut, *d_end, *d_ovf;
     uint32_t* d_co;
+    uint32_t* d_so;
     int64_t* d_bits;
     unsigned long long* d_mis;
     CU(cudaMalloc((void**)&d_sym, (size_t)C * stride));
@@ -57,6 +58,7 @@ int main(void) {
     CU(cudaMalloc((void**)&d_end, C * sizeof(int32_t)));
     CU(cudaMalloc((void**)&d_ovf, 2 * sizeof(int32_t)));   /* [0] encode overflow flag, [1] decode status */
     CU(cudaMalloc((void**)&d_co, (size_t)C * chunk_stride * sizeof(uint32_t)));
+    CU(cudaMalloc((void**)&d_so, (size_t)C * 8 * chunk_stride * sizeof(uint32_t)));
     CU(cudaMalloc((void**)&d_bits, C * sizeof(int64_t)));
     CU(cudaMalloc((void**)&d_mis, sizeof(unsigned long long)));
     CU(cudaMemcpy(d_sym, h_sym, (size_t)C * stride, cudaMemcpyHostToDevice));
@@ -68,9 +70,9 @@ int main(void) {
     CK(mua_calibrate(d_sym, NULL, NULL, stride, T, C, S, hH, 1, 1, MUA_WINDOW_TRUNCATE, d_tab, 1u, 0u,
                      d_cut, d_end, d_peak, d_enc, NULL, NULL, NULL, NULL, NULL));
     CK(mua_encode(d_sym, NULL, NULL, stride, T, C, S, d_cut, d_end, d_peak, d_enc, d_tab, K, 2, d_stream, slot, d_co,
-                  chunk_stride, d_bits, d_ovf, NULL, NULL));
-    CK(mua_decode(d_stream, slot, d_co, chunk_stride, NULL, stride, C, S, d_cut, d_end, d_peak, d_enc, d_tab, K, 2,
-                  H + T / 2, d_dec, d_ovf + 1, NULL, 0, NULL));
+                  chunk_stride, d_so, 8 * chunk_stride, d_bits, d_ovf, NULL, NULL));
+    CK(mua_decode(d_stream, slot, d_co, chunk_stride, d_so, 8 * chunk_stride, NULL, stride, C, S, d_cut, d_end, d_peak, d_enc,
+                  d_tab, K, 2, H + T / 2, d_dec, d_ovf + 1, NULL, 0, NULL));
     CK(mua_verify(d_sym, d_dec, NULL, stride, C, S, d_cut, d_end, d_mis, NULL));
     CU(cudaDeviceSynchronize());
 

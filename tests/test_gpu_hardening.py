@@ -125,7 +125,7 @@ def test_table_and_channel_state_mismatch_is_reported(sclv_tables):
     def raw_decode(K, Lmax, peak, enc):
         status.zero_()
         dec.fill_(0xEE)
-        _lib.check(lib.mua_decode(es.stream.data_ptr(), es.slot_bytes, es.chunk_off.data_ptr(), es.chunk_stride, None, rec.stride, C, S,
+        _lib.check(lib.mua_decode(es.stream.data_ptr(), es.slot_bytes, es.chunk_off.data_ptr(), es.chunk_stride, None, 0, None, rec.stride, C, S,
                                   st.data_ptr(), en.data_ptr(), peak.data_ptr(), enc.data_ptr(), cb.d_tables.data_ptr(), K, Lmax, 0,
                                   dec.data_ptr(), status.data_ptr(), None, 0, None))
         return int(status.item())
@@ -156,3 +156,51 @@ def test_table_and_channel_state_mismatch_is_reported(sclv_tables):
     d3 = torch.full_like(rec3.sym, 0xEE)
     P.decode(e3, rec3, cb3, st3, en3, bad3, ec3, out=d3, status=st_)
     assert int(st_.item()) == _lib.DEC_BAD_TABLE and bool((d3[5] == 0xEE).all())
+
+
+@pytest.mark.parametrize("H", [64, 100, 128, 1024, 7])
+def test_sub_chunk_side_info_matches_oracle_and_is_guarded(H, sclv_tables):
+    """the 128-symbol sub-chunk offsets of the chosen-system encoder (d_sub_off) against the oracle, written only for the
+    sub-chunks of every channel's window (guard columns / rows around the array survive), for window starts on and off the
+    64- and 128-symbol boundaries; the decode that uses them is lossless and touches nothing outside the window."""
+    S, C, T = 3, 77, 20000
+    thr = O.synth_threshold_table(50.0)
+    rec = P.synth_recording(C, T, seed=90 + H, BP_ms=50.0, bursty=True, device=DEV, thr=thr)
+    cb = mua_b200.Codebook(S, np.array([[1, 2, 2]]), device=DEV)
+    cal = P.calibrate(rec, cb, [H], use_sort=True, window="truncate")
+    st, en, pk, ec = (cal[k][:, 0].contiguous() for k in ("cutoff", "end", "peak", "enc"))
+    nchunk = (T + 1023) // 1024
+    ss = 8 * nchunk + 2
+    SENT = 0x7A5A5A5A
+    so_flat = torch.full(((C + 2) * ss,), SENT, dtype=torch.int32, device=DEV)
+    so = torch.as_strided(so_flat, (C, 8 * nchunk), (ss, 1), storage_offset=ss + 1)
+    es = P.encode(rec, cb, st, en, pk, ec)
+    es2 = P.EncodedStreams(stream=torch.zeros_like(es.stream), chunk_off=torch.zeros_like(es.chunk_off),
+                           total_bits=torch.zeros_like(es.total_bits), overflow=torch.zeros(1, dtype=torch.int32, device=DEV),
+                           slot_bytes=es.slot_bytes, chunk_stride=es.chunk_stride, sub_off=so)
+    P.encode(rec, cb, st, en, pk, ec, out=es2)
+    assert int(es2.overflow.item()) == 0
+    assert torch.equal(es2.chunk_off, es.chunk_off) and torch.equal(es2.total_bits, es.total_bits)
+    h = so_flat.cpu().numpy().view(np.uint32).reshape(C + 2, ss)
+    x = rec.sym.cpu().numpy()
+    stc, enc_, pkc = st.cpu().numpy(), en.cpu().numpy(), pk.cpu().numpy()
+    want_written = np.zeros((C + 2, ss), dtype=bool)
+    for c in range(C):
+        vals, written = O.sub_chunk_offsets(x[c, :T], int(stc[c]), int(enc_[c]), S, O.rank_of_symbol(int(pkc[c]), S), cb.lens[0])
+        n = len(vals)
+        want_written[c + 1, 1:1 + n] = written
+        assert np.array_equal(h[c + 1, 1:1 + n][written], vals[written]), c
+    assert (h[~want_written] == SENT).all(), "encoder wrote sub-chunk side info outside the window"
+    # decode through the sub-chunk decoder: lossless, nothing outside the window
+    guard_rows = 1
+    full = torch.full((C + 2 * guard_rows, rec.stride), 0xEE, dtype=torch.uint8, device=DEV)
+    dec = full[guard_rows:guard_rows + C]
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    P.decode(es2, rec, cb, st, en, pk, ec, out=dec, status=status)
+    assert int(status.item()) == 0
+    assert int(P.verify(rec, dec, S, st, en).item()) == 0
+    hh = full.cpu().numpy()
+    assert (hh[:guard_rows] == 0xEE).all() and (hh[guard_rows + C:] == 0xEE).all()
+    cols = np.arange(rec.stride)[None, :]
+    outside = (cols < stc[:, None]) | (cols >= enc_[:, None])
+    assert (hh[guard_rows:guard_rows + C][outside] == 0xEE).all()

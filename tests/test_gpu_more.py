@@ -79,7 +79,7 @@ def test_error_returns():
     assert rc == -1 and b"aligned" in lib.mua_last_error()
     with pytest.raises(_lib.MuaError):
         _lib.check(lib.mua_encode(buf.data_ptr(), None, None, 1000, 1000, 4, 3, None, None, None, None, None, 1, 2,
-                                  None, 16, None, 1, None, None, None, None))
+                                  None, 16, None, 1, None, 0, None, None, None, None))
     with pytest.raises(Exception):
         mua_b200.Codebook(3, np.array([[1, 1, 2]]), device=DEV)  # not a complete prefix code
 
