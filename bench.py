@@ -446,9 +446,11 @@ def run_b200(a):
     else:
         peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     n_chunks = int(((en + 1023) // 1024 - st // 1024).clamp(min=0).sum().item())
-    side = 4 * n_chunks + 8 * C
+    n_sub = int(((en + 127) // 128 - st // 128).clamp(min=0).sum().item()) if es.sub_off is not None and cb.S <= 3 and cb.Lmax <= 2 else 0
+    sub_decode = n_sub > 0 and (max_end + 1023) // 1024 >= 8  # mua_decode's rule for the sub-chunk decoder (needs the 128-symbol offsets)
+    side = 4 * n_chunks + 4 * n_sub + 8 * C                   # chunk offsets, 128-symbol sub-chunk offsets (fast encoder), bit counts
     enc_bytes = nsym_local + bits_local / 8 + side            # symbols read + stream written + side info
-    dec_bytes = bits_local / 8 + nsym_local + 4 * n_chunks    # stream read + symbols written + offsets read
+    dec_bytes = bits_local / 8 + nsym_local + (4 * n_sub if sub_decode else 4 * n_chunks)   # stream read + symbols written + offsets read
     cal_bytes = float(C) * min(T, (max(HS) + T // 2) if W["name"] == "cfg4" else H_)   # bins scanned by the calibrate pass
     stages = {"calibrate_ms": float(stage_ms[0]), "encode_ms": float(stage_ms[1]), "decode_ms": float(stage_ms[2]),
               "gather_ms": float(stage_ms[3]),   # N > 1: what is left of the report exchange after the decode it overlaps
@@ -460,7 +462,9 @@ def run_b200(a):
               "bits_per_symbol": bits_local / max(nsym_local, 1),
               "per_step_ms": {"calibrate": [round(float(v), 4) for v in stage_all[:, 0]], "encode": [round(float(v), 4) for v in stage_all[:, 1]],
                               "decode": [round(float(v), 4) for v in stage_all[:, 2]], "gather": [round(float(v), 4) for v in stage_all[:, 3]]}}
-    names = W["kernels"]
+    names = list(W["kernels"])
+    if sub_decode:
+        names[2] = "k_decode_sub"
     order = np.argsort([-stage_ms[0], -stage_ms[1], -stage_ms[2]])
     di = int(order[0])
     dom = names[di]

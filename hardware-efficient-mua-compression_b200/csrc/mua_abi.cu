@@ -48,6 +48,21 @@ int sm_count() {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda): the tensor view of a decoded buffer for k_decode_sub
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeTiledFn tensor_map_encoder() {
+    static TensorMapEncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<TensorMapEncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
 int check_layout(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C) {
     REQUIRE(C >= 0, "C < 0");
     REQUIRE(d_sym != nullptr || C == 0, "d_sym is NULL");      // a recording without channels has no buffer
@@ -477,6 +492,8 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     REQUIRE(aligned16(d_stream) && slot_bytes > 0 && slot_bytes % 16 == 0, "d_stream/slot_bytes must be 16-byte aligned");
     REQUIRE(chunk_stride >= (T + TILE - 1) / TILE && chunk_stride >= 1, "chunk_stride < ceil(T/%d)", TILE);
     REQUIRE(!d_sub_off || sub_stride >= 8 * ((T + TILE - 1) / TILE), "sub_stride < 8 * ceil(T/%d)", TILE);
+    REQUIRE((long long)C * chunk_stride < (1ll << 29) && (!d_sub_off || (long long)C * sub_stride < (1ll << 29)),
+            "side-info arrays must be smaller than 2 GiB");
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 0) return MUA_OK;
     REQUIRE(S >= 2 && S <= MUA_MAX_S && K >= 1 && K <= MUA_MAX_K && Lmax >= 1 && Lmax <= 9, "bad S/K/Lmax");
@@ -639,11 +656,24 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
             const long long sgroups = (long long)C * ((8 * P.item_chunks + 31) / 32);
             if (MUA_DEC_SUB && d_sub_off && !d_off && h.S <= 3 && P.item_chunks >= MUA_DEC_SUB_MIN_CHUNKS && sgroups < (1ll << 31)) {
                 REQUIRE(sub_stride >= 8 * P.item_chunks, "sub_stride < 8 * chunks per channel");
+                DecSubParams PS;
+                PS.D = P;
+                memset(&PS.tmap, 0, sizeof(PS.tmap));
+#if MUA_DS_TMA
+                REQUIRE(tensor_map_encoder() != nullptr, "cuTensorMapEncodeTiled is not available");
+                const cuuint64_t gdim[3] = {128, (cuuint64_t)((stride + 127) / 128), (cuuint64_t)C};
+                const cuuint64_t gstr[2] = {128, (cuuint64_t)stride};
+                const cuuint32_t box[3] = {128, 32, 1}, estr[3] = {1, 1, 1};
+                const CUresult r = tensor_map_encoder()(&PS.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d_dec, gdim, gstr, box, estr,
+                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+#endif
                 cudaError_t e = cudaFuncSetAttribute(k_decode_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM);
                 if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
                 const long long blocks_needed = (sgroups + DS_WARPS - 1) / DS_WARPS;
                 const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
-                k_decode_sub<<<grid, DS_WARPS * 32, DL_SMEM, st>>>(P);
+                k_decode_sub<<<grid, DS_WARPS * 32, DL_SMEM, st>>>(PS);
                 CHECK_LAUNCH("k_decode");
                 return MUA_OK;
             }

@@ -1,6 +1,8 @@
 // Stage 6: table-driven chunk-parallel decode (one lane per 1024-symbol chunk, multi-symbol LUT),
 // the device-side round-trip check, the synthetic MUA generator and the binning kernels (stage 1).
 #pragma once
+#include <cuda.h>
+
 #include "mua_common.cuh"
 
 namespace mua {
@@ -887,19 +889,42 @@ __global__ void __launch_bounds__(DL_WARPS / NC * 32, 1) k_decode_lane(const __g
 //     128-byte-swizzled tile (piece q of row l at position q ^ (l & 7): conflict-free for the lanes' stores and for the write-out);
 //   * the 32 lanes' stream bytes are consecutive too (<= 1 KB + slack): the warp copies them with cp.async (16 bytes per lane and
 //     round) into one of two staging buffers, one group ahead; no per-lane ring, no top-ups, no refill bookkeeping beyond a pointer;
-//   * per-warp shared memory drops to 7 KB and the state of a lane to a handful of registers: 24 warps (768 chains) per SM.
+//   * per-warp shared memory drops to 6.1 KB and the state of a lane to a handful of registers: 28 warps (896 chains) per SM (30 or 31 fit and are no faster).
 // Same lane-private-bank tables, rank -> symbol PRMT and lookup chain as k_decode_lane.  Groups never span channels (a channel's
 // sub-chunks are padded to a multiple of 32); the side info of the next two groups and the stream of the next group are requested
 // while the current group is decoded.  Partial sub-chunks (window start / end inside) and rows that are not 16-byte aligned take
 // a per-row path with predicated, alignment-dependent stores.
 #ifndef MUA_DS_WARPS
-#define MUA_DS_WARPS 26
+#define MUA_DS_WARPS 28
 #endif
 constexpr int DS_WARPS = MUA_DS_WARPS;
-constexpr int DS_STR_B = 1536;                     // staged stream bytes per group: 32 sub-chunks of <= 32 bytes + alignment + look-ahead
+constexpr int DS_STR_B = 1088;                     // staged stream bytes per group: 31 x 32 B between the first and the last lane's
+                                                   // first byte + 15 (alignment) + 48 + 15 (last lane's words, rounded up) <= 1072
 constexpr int DS_TILE_B = 32 * 128;
-constexpr int DS_UNIT_B = DS_TILE_B + 2 * DS_STR_B;   // per warp: tile (1024-byte aligned), two stream buffers
-static_assert(DS_UNIT_B % 1024 == 0, "units keep the tiles 1024-byte aligned");
+
+// Shared memory of k_decode_sub: [rank maps + ticket: 128 B] ... [K tables at the first 32 KB boundary] ...; the n warps' tiles
+// (4 KB, 1024-byte aligned: the swizzle) and then their pairs of stream buffers are bump-allocated below the tables first, then
+// above them.  Returns false when warp w's buffers do not fit.
+__device__ __forceinline__ bool ds_layout(int n, int w, uint32_t base_a, uint32_t tab_a, uint32_t hi_a, uint32_t end_a, uint32_t& tile,
+                                          uint32_t& str) {
+    uint32_t lo = (base_a + 1023u) & ~1023u, hi = hi_a;
+    tile = 0; str = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t a;
+        if (lo + DS_TILE_B <= tab_a) { a = lo; lo += DS_TILE_B; }
+        else if (hi + DS_TILE_B <= end_a) { a = hi; hi += DS_TILE_B; }
+        else return false;
+        if (i == w) tile = a;
+    }
+    for (int i = 0; i < n; ++i) {
+        uint32_t a;
+        if (lo + 2 * DS_STR_B <= tab_a) { a = lo; lo += 2 * DS_STR_B; }
+        else if (hi + 2 * DS_STR_B <= end_a) { a = hi; hi += 2 * DS_STR_B; }
+        else return false;
+        if (i == w) str = a;
+    }
+    return true;
+}
 
 struct DsRaw {               // the loads of one lane's sub-chunk bookkeeping, nothing derived yet
     int c, mrel, valid;
@@ -911,8 +936,20 @@ struct DsItem {
     uint32_t bitoff;         // bit offset of its first symbol in the channel's stream
     uint8_t* optr;           // where its first symbol goes
     const uint8_t* sbase;    // the channel's slot
-    int pk, en;
+    uint32_t info;           // peak | SCLV row << 4 | (window start / 1024) << 12
 };
+
+// the decoded buffer as a tensor for the TMA engine: uint8 [C][stride / 128][128], box 128 x 32 x 1, 128-byte swizzle
+struct DecSubParams {
+    DecParams D;
+    alignas(64) CUtensorMap tmap;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src_smem), "r"(x),
+                 "r"(y), "r"(z)
+                 : "memory");
+}
 
 __device__ __forceinline__ DsRaw ds_load(const DecParams& P, uint32_t g, uint32_t ngroups, uint32_t gpc, int lane) {
     DsRaw r;
@@ -931,7 +968,7 @@ __device__ __forceinline__ DsRaw ds_load(const DecParams& P, uint32_t g, uint32_
 __device__ __forceinline__ DsItem ds_finish(const DecParams& P, DsRaw r, int K, int S) {
     asm volatile("" : "+r"(r.start), "+r"(r.end), "+r"(r.pk), "+r"(r.en), "+r"(r.sub));
     DsItem it;
-    it.rem = 0; it.bitoff = 0; it.optr = P.dec; it.sbase = P.stream; it.pk = 0; it.en = 0;
+    it.rem = 0; it.bitoff = 0; it.optr = P.dec; it.sbase = P.stream; it.info = 0;
     if (r.valid && r.end > r.start && r.start >= 0) {
         const int mabs = 8 * (r.start >> 10) + r.mrel;                 // absolute sub-chunk index
         const int a = max(r.start, mabs << 7), b = min(r.end, (mabs << 7) + 128);
@@ -946,16 +983,19 @@ __device__ __forceinline__ DsItem ds_finish(const DecParams& P, DsRaw r, int K, 
                 it.bitoff = bo;
                 it.sbase = P.stream + (size_t)r.c * P.slot_bytes;
                 it.optr = P.dec + (long long)r.c * P.stride + a;
-                it.pk = r.pk;
-                it.en = r.en;
+                it.info = (uint32_t)r.pk | ((uint32_t)r.en << 4) | ((uint32_t)(r.start >> 10) << 12);
             }
         }
     }
     return it;
 }
 
-__global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_constant__ DecParams P) {
+#ifndef MUA_DS_TMA
+#define MUA_DS_TMA 1        // complete groups leave through one TMA tensor store (0: 16-byte stores from the tile)
+#endif
+__global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_constant__ DecSubParams PS) {
     extern __shared__ __align__(1024) uint8_t dsm[];
+    const DecParams& P = PS.D;
     const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
     const int K = T->K;
     if (T->S != P.S || K != P.K || T->Lmax != P.Lmax || T->nsym != 4 || T->W != 8 || K > DL_MAX_ROWS || T->S > 8 || P.off != nullptr ||
@@ -967,13 +1007,17 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // ---- shared-memory layout: rank -> symbol maps + ticket, per-warp units below and above the tables (32 KB aligned) ----
     const uint32_t map_a = smem_u32(dsm);                         // uint2 [8]: idx[p][0..7]; word 16: ticket
-    const uint32_t base_a = (map_a + 128 + 1023) & ~1023u;
+    const uint32_t base_a = map_a + 128;
     const uint32_t tab_a = (map_a + 128 + (DL_TAB_B - 1)) & ~(uint32_t)(DL_TAB_B - 1);
     const uint32_t hi_a = tab_a + K * DL_TAB_B;
     const uint32_t end_a = map_a + DL_SMEM;
-    const int n_low = tab_a > base_a ? (int)((tab_a - base_a) / DS_UNIT_B) : 0;
-    const int n_high = hi_a <= end_a ? (int)((end_a - hi_a) / DS_UNIT_B) : 0;
-    const int nw = min((int)(blockDim.x >> 5), n_low + n_high);  // warps that have their buffers
+    uint32_t tile_a = 0, str_a = 0;
+    int nw = (int)(blockDim.x >> 5);                              // warps that have their buffers
+    while (nw > 0 && !ds_layout(nw, nw - 1, base_a, tab_a, hi_a, end_a, tile_a, str_a)) --nw;
+    if (nw == 0 || hi_a > end_a) {
+        if (threadIdx.x == 0) dec_flag(P.status, MUA_DEC_BAD_TABLE);
+        return;
+    }
     {
         uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm + (tab_a - map_a));
         const int nword = K * 256 * 32;
@@ -994,9 +1038,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_co
     }
     __syncthreads();
     if (warp >= nw) return;
-    const uint32_t unit_a = warp < n_low ? base_a + warp * DS_UNIT_B : hi_a + (warp - n_low) * DS_UNIT_B;
-    const uint32_t tile_a = unit_a;
-    const uint32_t str_a = unit_a + DS_TILE_B;                    // two buffers of DS_STR_B bytes
+    ds_layout(nw, warp, base_a, tab_a, hi_a, end_a, tile_a, str_a);   // this warp's tile and its two stream buffers of DS_STR_B bytes
     const uint32_t* s_str = reinterpret_cast<const uint32_t*>(dsm + (str_a - map_a));
     const int col8 = lane & 7, row4 = lane >> 3;
     const uint32_t gpc = (uint32_t)((8 * P.item_chunks + 31) / 32);   // groups per channel
@@ -1038,9 +1080,9 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_co
     stage(nxt, 1, lo_nxt);
     while (g0 < ngroups) {
         // ---- this group's lane state ----
-        const uint32_t lbase = tab_a + (uint32_t)cur.en * DL_TAB_B + lane * 4;       // this lane's bank of its row's table
+        const uint32_t lbase = tab_a + ((cur.info >> 4) & 0xFFu) * DL_TAB_B + lane * 4;   // this lane's bank of its row's table
         uint32_t mlo, mhi;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mlo), "=r"(mhi) : "r"(map_a + cur.pk * 8));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mlo), "=r"(mhi) : "r"(map_a + (cur.info & 0xFu) * 8));
         const int rem = cur.rem;
         const unsigned long long optr_self = reinterpret_cast<unsigned long long>(cur.optr);
         const uint32_t* sp = s_str + buf * (DS_STR_B / 4);
@@ -1051,6 +1093,10 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_co
         uint32_t w0 = stream_rev(sp[rp]), w1 = stream_rev(sp[rp + 1]), wn = sp[rp + 2];
         rp += 3;
         const uint32_t trow_a = tile_a + lane * 128;
+#if MUA_DS_TMA
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the TMA engine has read the previous group's tile
+        __syncwarp();
+#endif
         // ---- 128 symbols per lane into the tile ----
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -1092,6 +1138,16 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_co
         // ---- write-out ----
         if (__all_sync(FULL, rem == 128)) {
             // 32 complete sub-chunks of one channel: 4 KB of consecutive symbols
+#if MUA_DS_TMA
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lanes' tile stores, before the TMA engine reads them
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t ch = g0 / gpc;
+                tma_store_3d(&PS.tmap, tile_a, 0, (int)(8u * (cur.info >> 12) + (g0 - ch * gpc) * 32u), (int)ch);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else if (false) {
+#endif
             uint8_t* d0 = reinterpret_cast<uint8_t*>(__shfl_sync(FULL, optr_self, 0));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1135,6 +1191,9 @@ __global__ void __launch_bounds__(DS_WARPS * 32, 1) k_decode_sub(const __grid_co
         g0 = g1; g1 = g2; g2 = g3;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#if MUA_DS_TMA
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
     dec_wait_report(P);
 }
 

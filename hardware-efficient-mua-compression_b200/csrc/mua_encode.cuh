@@ -436,16 +436,20 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
             uint32_t* co = P.chunk_off + (size_t)c * P.chunk_stride - start / TILE;
             if (lane == 0) co[start / TILE] = 0;
             // full tiles: the two absolute multiples of 1024 inside a tile are the first symbols of the same two lanes in every
-            // tile of the channel (the tile origin is a multiple of 64)
+            // tile of the channel (the tile origin is a multiple of 64); every second lane starts a 128-symbol sub-chunk.  The
+            // lane's side-info slots are kept as 32-bit BYTE offsets into the arrays (the host checks that they fit; the kernel
+            // sits at its register limit and would otherwise rebuild two 64-bit addresses per tile): slot in tile 0, +8 / +64
+            // bytes per tile; bit 31 set = this lane writes nothing.
             const int l1 = ((-A0) & (TILE - 1)) >> 6;      // 0..15
-            const bool own_b = (lane & 15) == l1;          // this lane starts a chunk (lanes l1 and l1 + 16)
-            uint32_t* co_l = co + ((A0 + 64 * l1 + (lane >> 4) * TILE) >> 10);   // its side-info slot in tile 0 (+2 per tile)
-            // 128-symbol sub-chunk side info (for the sub-chunk decoder): entry 8 j + i = bit offset of sub-chunk i of chunk j; in a
-            // full tile every second lane starts a sub-chunk
+            const uint32_t co_b = (lane & 15) == l1
+                                      ? 4u * (uint32_t)((size_t)c * P.chunk_stride + ((A0 + 64 * l1 + (lane >> 4) * TILE) >> 10) - start / TILE)
+                                      : 0x80000000u;
+            // 128-symbol sub-chunk side info (for the sub-chunk decoder): entry 8 j + i = bit offset of sub-chunk i of chunk j
             uint32_t* so = P.sub_off ? P.sub_off + (size_t)c * P.sub_stride - 8 * (start / TILE) : nullptr;
             if (so && lane == 0) so[start >> 7] = 0;                             // the sub-chunk that holds the window start
-            const bool own_s = so && (((A0 >> 6) + lane) & 1) == 0;
-            uint32_t* so_l = so + ((A0 + 64 * lane) >> 7);                       // its slot in tile 0 (+16 per tile)
+            const uint32_t so_b = (so && (((A0 >> 6) + lane) & 1) == 0)
+                                      ? 4u * (uint32_t)((size_t)c * P.sub_stride + ((A0 + 64 * lane) >> 7) - 8 * (start / TILE))
+                                      : 0x80000000u;
             uint8_t* out = P.stream + (size_t)c * P.slot_bytes;
             uint32_t carry = 0;
 
@@ -471,8 +475,8 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
                 if (full) {
                     enc_fast_pieces<SV>(tile_w + lane * 64, lut_saddr, lane, pc, pl);
                     enc_fast_place<true, RM>(pc, pl, lane, s_ring, Pbits, carry, a_lane);
-                    if (own_b) co_l[2 * t] = a_lane;
-                    if (own_s) so_l[16 * t] = a_lane;
+                    if ((int)co_b >= 0) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(P.chunk_off) + (co_b + 8u * (uint32_t)t)) = a_lane;
+                    if ((int)so_b >= 0) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(P.sub_off) + (so_b + 64u * (uint32_t)t)) = a_lane;
                 } else {
                     // partial tile: k 16-symbol pieces per lane cover what is left of the window
                     const int k = min(4, (end - ts + 511) >> 9);

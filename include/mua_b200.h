@@ -221,7 +221,8 @@ int mua_report_wait(const mua_report_sink* h_sink, int32_t step, void* stream);
 /* Encode window [d_start[c], d_end[c]) (d_end <= len; d_end <= d_start encodes nothing) of every
  * channel with rank map of d_peak[c] and codebook row d_enc[c].
  *   d_stream      : C slots of `slot_bytes` (multiple of 16); slot c holds the padded stream
- *   d_chunk_off   : uint32 [C][chunk_stride]; entry j = bit offset of chunk j (see header comment)
+ *   d_chunk_off   : uint32 [C][chunk_stride]; entry j = bit offset of chunk j (see header comment); this array and
+ *                   d_sub_off must each be smaller than 2 GiB
  *   d_total_bits  : int64 [C]  (== SCLV[enc] . mapped post histogram, get_BR_no_sort.py:287)
  *   d_overflow    : int32 [1], MUA_ENC_OVERFLOW when a stream did not fit its slot, MUA_ENC_BAD_TABLE when
  *                   S/K/Lmax do not match the table block or a channel's peak/row is out of range
