@@ -248,10 +248,11 @@ class EncodedStreams:
 
 
 def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None, out: EncodedStreams = None, sink=None,
-           sub_offsets: bool = True):
+           sub_offsets: Optional[bool] = None):
     """Stage 5 (mua_encode): window [start[c], end[c]) of every channel -> per-channel bitstreams.
     sub_offsets: also allocate the 128-symbol sub-chunk side info (written for codebooks with Lmax <= 2, S <= 3; see
-    include/mua_b200.h) that lets mua_decode write consecutive symbols.
+    include/mua_b200.h) that lets mua_decode write consecutive symbols.  Default: only where the decoder can use it -- that
+    codebook class and rows long enough for windows of eight chunks and more (T >= 16384).
     sink: a `_lib.ReportSink` (dist.PeerReport.sink(step)): every channel's report row is also stored into all peers' buffers."""
     lib = _lib.load()
     dev = rec.device
@@ -260,6 +261,8 @@ def encode(rec: Recording, cb: Codebook, start, end, peak, enc, slot_bytes=None,
     peak = peak.to(torch.uint8).contiguous()
     enc = enc.to(torch.uint8).contiguous()
     chunk_stride = max(1, (rec.T + CHUNK - 1) // CHUNK)
+    if sub_offsets is None:
+        sub_offsets = cb.S <= 3 and cb.Lmax <= 2 and rec.T >= 16 * CHUNK
     if out is None:
         if slot_bytes is None:
             slot_bytes = cb.worst_case_slot_bytes(rec.T)
