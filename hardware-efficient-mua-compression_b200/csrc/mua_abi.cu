@@ -1,12 +1,14 @@
 // C ABI of libmua_b200.so (see include/mua_b200.h): argument validation + kernel launches.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mua_calibrate.cuh"
 #include "mua_decode.cuh"
 #include "mua_dropin.cuh"
 #include "mua_encode.cuh"
+#include "mua_encode_rows.cuh"
 
 using namespace mua;
 
@@ -44,6 +46,15 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached > 0 ? cached : 148;
+}
+
+// rows of at most this many bins are encoded by the lane-per-channel kernels (MUA_ROWS_T overrides it for A/B measurements)
+int rows_t_max() {
+    static const int v = [] {
+        const char* e = getenv("MUA_ROWS_T");
+        return e ? atoi(e) : 16384;
+    }();
+    return v;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -528,7 +539,37 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         }
     }
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
-    if (h.Lmax <= 2 && S <= 3) {
+    if (h.Lmax <= 2 && S <= 3 && T <= rows_t_max() && S * K * EF_LUT_B <= ER_LUT_MAX) {
+        // short rows: a lane per channel.  All 32-channel blocks of a wave are resident at once; the warps are spread evenly
+        // over the waves (a block is a long task: an extra, nearly empty wave would cost as much as a full one)
+        const int smem = EncRowsSmem::TOTAL;
+        const bool fixed = !d_off && !d_len && T > 0 && tensor_map_encoder() != nullptr;
+        EncRowsParams PR;
+        PR.E = P;
+        memset(&PR.tmap, 0, sizeof(PR.tmap));
+        if (fixed) {   // the recording as a 2-D tensor for the TMA engine: bin x channel, boxes of 128 bins x 32 channels
+            const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)C};
+            const cuuint64_t gstr[1] = {(cuuint64_t)stride};
+            const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
+            const CUresult r = tensor_map_encoder()(&PR.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(d_sym), gdim, gstr, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        }
+        const long long nblk = ((long long)C + 31) / 32;
+        const int grid = (int)(nblk < sm_count() ? nblk : sm_count());
+        const long long per_sm = (nblk + grid - 1) / grid, rounds = (per_sm + ER_WARPS - 1) / ER_WARPS;
+        PR.wuse = (int32_t)((per_sm + rounds - 1) / rounds);
+#define MUA_LAUNCH_ENCR(SV, FX)                                                                                         \
+    do {                                                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(k_encode_rows<SV, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                            \
+        k_encode_rows<SV, FX><<<grid, ER_WARPS * 32, smem, st>>>(PR);                                                   \
+    } while (0)
+        if (S == 2) { if (fixed) MUA_LAUNCH_ENCR(2, true); else MUA_LAUNCH_ENCR(2, false); }
+        else { if (fixed) MUA_LAUNCH_ENCR(3, true); else MUA_LAUNCH_ENCR(3, false); }
+#undef MUA_LAUNCH_ENCR
+    } else if (h.Lmax <= 2 && S <= 3) {
         const int smem = EncFastSmem::PER_WARP * EF_WARPS;
         const int per_sm = 4;
         const int need = (C + EF_WARPS - 1) / EF_WARPS;
