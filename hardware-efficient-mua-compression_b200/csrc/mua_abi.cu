@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "mua_calibrate.cuh"
+#include "mua_calibrate_rows.cuh"
 #include "mua_decode.cuh"
 #include "mua_dropin.cuh"
 #include "mua_encode.cuh"
@@ -48,15 +49,6 @@ int sm_count() {
     return cached > 0 ? cached : 148;
 }
 
-// rows of at most this many bins are encoded by the lane-per-channel kernels (MUA_ROWS_T overrides it for A/B measurements)
-int rows_t_max() {
-    static const int v = [] {
-        const char* e = getenv("MUA_ROWS_T");
-        return e ? atoi(e) : 16384;
-    }();
-    return v;
-}
-
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda): the tensor view of a decoded buffer for k_decode_sub
@@ -72,6 +64,22 @@ TensorMapEncodeTiledFn tensor_map_encoder() {
         return reinterpret_cast<TensorMapEncodeTiledFn>(p);
     }();
     return fn;
+}
+
+// rows of at most this many bins are encoded by the lane-per-channel kernels (MUA_ROWS_T overrides it for A/B measurements)
+int rows_t_max() {
+    static const int v = [] {
+        const char* e = getenv("MUA_ROWS_T");
+        return e ? atoi(e) : 16384;
+    }();
+    return v;
+}
+
+// ... and only for recordings with at least this many channels: a warp takes 32 channels, so the lane-per-channel kernels need
+// ~8 blocks per SM to keep the SMs busy (MUA_ROWS_MIN_C overrides it, read at every call: the tests switch kernel families with it)
+int rows_min_channels() {
+    const char* e = getenv("MUA_ROWS_MIN_C");
+    return e ? atoi(e) : 8 * 32 * sm_count();
 }
 
 int check_layout(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len, int64_t stride, int32_t T, int32_t C) {
@@ -127,6 +135,62 @@ void launch_calibrate_head(const CalibParams& P, cudaStream_t st) {
     }
 }
 
+template <int S>
+int launch_calibrate_rows(const CalibParams& P, cudaStream_t st) {
+    CalRowsParams PR;
+    memset(&PR, 0, sizeof(PR));
+    PR.C = P;
+    const int T = P.L.T, nH = P.nH;
+    // the boundaries of every channel (all rows are T bins long), sorted: cutoffs that a post window follows keep their counts
+    struct Ev { int pos, kind, h; } ev[2 * MUA_MAX_H];
+    int nev = 0;
+    for (int h = 0; h < nH; ++h) {
+        const int cut = T < (P.H[h] > 1 ? P.H[h] : 1) ? T : (P.H[h] > 1 ? P.H[h] : 1);   // functions_1.py:59-68
+        int end = 0;
+        if (P.mode == MUA_WINDOW_SKIP) {
+            end = cut + T / 2;                                                           // get_BR_no_sort.py:178-183
+            if (end > T) end = -1;
+        } else if (P.mode == MUA_WINDOW_TRUNCATE) {
+            end = cut + T / 2 < T ? cut + T / 2 : T;                                     // test_chosen_system.py:99-103
+        }
+        const bool has_post = end > 0 && P.mode != MUA_WINDOW_NONE && P.need_post;
+        PR.cutv[h] = cut;
+        PR.endv[h] = P.mode == MUA_WINDOW_NONE ? cut : end;
+        if (has_post) {
+            ev[nev++] = Ev{cut, CR_EV_STORE, h};
+            ev[nev++] = Ev{end, CR_EV_END, h};
+        } else {
+            ev[nev++] = Ev{cut, CR_EV_CUT_ONLY, h};
+        }
+    }
+    for (int i = 1; i < nev; ++i)   // insertion sort by (position, kind)
+        for (int j = i; j > 0 && (ev[j].pos < ev[j - 1].pos || (ev[j].pos == ev[j - 1].pos && ev[j].kind < ev[j - 1].kind)); --j) {
+            const Ev t = ev[j]; ev[j] = ev[j - 1]; ev[j - 1] = t;
+        }
+    PR.nev = nev;
+    for (int i = 0; i < nev; ++i) { PR.ev_pos[i] = ev[i].pos; PR.ev_kind[i] = (uint8_t)ev[i].kind; PR.ev_h[i] = (uint8_t)ev[i].h; }
+    PR.per_warp = 2 * CalRowsSmem::STAGE + ((nH * (S - 1) * 64 + 1023) / 1024) * 1024;
+    int warps = (227 * 1024 - CalRowsSmem::WARP0) / PR.per_warp;
+    if (warps > CR_MAX_WARPS) warps = CR_MAX_WARPS;
+    const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)P.L.C};
+    const cuuint64_t gstr[1] = {(cuuint64_t)P.L.stride};
+    const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
+    const CUresult r = tensor_map_encoder()(&PR.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(P.L.sym), gdim, gstr, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const long long nblk = ((long long)P.L.C + 31) / 32;
+    const int grid = (int)(nblk < sm_count() ? nblk : sm_count());
+    const long long per_sm = (nblk + grid - 1) / grid, rounds = (per_sm + warps - 1) / warps;
+    PR.wuse = (int32_t)((per_sm + rounds - 1) / rounds);
+    const int smem = CalRowsSmem::WARP0 + warps * PR.per_warp;
+    cudaError_t e = cudaFuncSetAttribute(k_calibrate_rows<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "calibrate smem attribute");
+    k_calibrate_rows<S><<<grid, warps * 32, smem, st>>>(PR);
+    CHECK_LAUNCH("k_calibrate_rows");
+    return MUA_OK;
+}
+
 // one alphabet size: the scan counts exactly its thresholds; several: one scan with the thresholds of the largest
 int dispatch_calibrate(const CalibParams& P, cudaStream_t st) {
     if (P.L.C == 0) return MUA_OK;
@@ -146,6 +210,22 @@ int dispatch_calibrate(const CalibParams& P, cudaStream_t st) {
         }
         CHECK_LAUNCH("k_calibrate_head");
         return MUA_OK;
+    }
+    if (P.nS == 1 && !P.train && !P.L.off && !P.L.len && P.L.T > 0 && P.L.T <= (rows_t_max() < 16384 ? rows_t_max() : 16384) &&
+        P.L.C >= rows_min_channels() && tensor_map_encoder() != nullptr) {
+        // many short rows of one length: a lane per channel (k_calibrate_rows); all boundaries are the same bins for every channel
+        switch (P.out[0].S) {
+            case 2: return launch_calibrate_rows<2>(P, st);
+            case 3: return launch_calibrate_rows<3>(P, st);
+            case 4: return launch_calibrate_rows<4>(P, st);
+            case 5: return launch_calibrate_rows<5>(P, st);
+            case 6: return launch_calibrate_rows<6>(P, st);
+            case 7: return launch_calibrate_rows<7>(P, st);
+            case 8: return launch_calibrate_rows<8>(P, st);
+            case 9: return launch_calibrate_rows<9>(P, st);
+            case 10: return launch_calibrate_rows<10>(P, st);
+            default: return fail(MUA_E_INVALID, "S=%d outside 2..10", P.out[0].S);
+        }
     }
     if (P.nS == 1) {
         switch (P.out[0].S) {
@@ -539,13 +619,14 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         }
     }
     const int ctas_needed = (C + ENC_WARPS - 1) / ENC_WARPS;
-    if (h.Lmax <= 2 && S <= 3 && T <= rows_t_max() && S * K * EF_LUT_B <= ER_LUT_MAX) {
+    if (h.Lmax <= 2 && S <= 3 && T <= rows_t_max() && C >= rows_min_channels() && S * K * EF_LUT_B <= ER_LUT_MAX) {
         // short rows: a lane per channel.  All 32-channel blocks of a wave are resident at once; the warps are spread evenly
         // over the waves (a block is a long task: an extra, nearly empty wave would cost as much as a full one)
         const int smem = EncRowsSmem::TOTAL;
         const bool fixed = !d_off && !d_len && T > 0 && tensor_map_encoder() != nullptr;
         EncRowsParams PR;
         PR.E = P;
+        PR.zero = 0;
         memset(&PR.tmap, 0, sizeof(PR.tmap));
         if (fixed) {   // the recording as a 2-D tensor for the TMA engine: bin x channel, boxes of 128 bins x 32 channels
             const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)C};

@@ -1,0 +1,248 @@
+// Stages 2-4 for recordings of many SHORT rows: a LANE per channel (the calibrate companion of k_encode_rows).
+//
+// k_calibrate (a warp per channel) serves all history lengths of a channel from one scan, but on a 2 400-bin row nearly every
+// 512-byte tile holds a boundary and takes the warp-wide snapshot path (REDUX + lane scan + shuffles): ~1 350 (S = 3) to
+// ~3 300 (S = 9) warp instructions per channel, 0.1-0.2 of the HBM roofline.  Here a warp owns 32 channels of a fixed-stride
+// recording (all rows T bins long, so every cutoff and window end is the SAME bin for all lanes):
+//   * rows are staged by the TMA engine exactly as in k_encode_rows: boxes of 128 bins x 32 channels, 128-byte swizzle, two
+//     stages per warp, mbarrier completion; lane l reads its own row conflict-free;
+//   * every lane keeps the cumulative counts #{x >= v} (v = 1..S-1) of ITS channel in registers: per 4 bytes and threshold
+//     one add, one LOP3 and one DP4A (the SWAR threshold compare of k_calibrate), no cross-lane traffic at all;
+//   * the boundaries are a host-sorted list of warp-uniform events.  A boundary inside a 64-bin step costs one masked
+//     recount of that step (same three instructions per word, byte mask from the uniform datapath); a cutoff stores the
+//     lane's counts as uint16 in its own shared-memory column, a window end (or a cutoff without post window) finishes
+//     (channel, history length) on the spot: histograms as count differences, first argmax, SCLV costs with the rank map
+//     applied by a data-dependent PRMT on the 16-byte length row (one PRMT + one IMAD per row and symbol), first argmin, bit
+//     count -- the epilogue of k_calibrate, one lane per channel.
+// Results are those of k_calibrate (same oracle, same tests; every GPU test runs with both kernel families).
+#pragma once
+#include <cuda.h>
+
+#include "mua_calibrate.cuh"
+#include "mua_encode_rows.cuh"
+
+namespace mua {
+
+constexpr int CR_MAX_WARPS = 24;
+constexpr int CR_EV_STORE = 0;      // cutoff followed by a post window: keep the counts
+constexpr int CR_EV_END = 1;        // window end: finish (channel, h) with the kept counts
+constexpr int CR_EV_CUT_ONLY = 2;   // cutoff without post window (window NONE / skipped channel / post outputs not wanted)
+
+struct CalRowsParams {
+    CalibParams C;
+    int32_t wuse;                        // warps of a CTA that take blocks
+    uint32_t zero;                       // == 0, opaque to the compiler (see k_encode_rows: ties a TMA request to the stage's last reads)
+    int32_t nev;                         // events, sorted by position (stores before ends at equal positions)
+    int32_t ev_pos[2 * MUA_MAX_H];
+    uint8_t ev_kind[2 * MUA_MAX_H], ev_h[2 * MUA_MAX_H];
+    int32_t cutv[MUA_MAX_H], endv[MUA_MAX_H];   // what d_cutoff / d_end receive
+    int32_t per_warp;                    // shared-memory bytes per warp: two stages + the kept counts
+    alignas(64) CUtensorMap tmap;
+};
+
+struct CalRowsSmem {
+    static constexpr int LEN = 0;                        // MUA_MAX_K x 16 B SCLV rows
+    static constexpr int RANK = LEN + MUA_MAX_K * 16;    // MUA_MAX_S x 16 B rank maps
+    static constexpr int BARS = RANK + MUA_MAX_S * 16;   // 2 mbarriers per warp
+    static constexpr int WARP0 = 2048;
+    static constexpr int STAGE = 4096;
+    static constexpr int SNAP = 2 * STAGE;               // uint16 [nH][S - 1][32 lanes]
+};
+static_assert(CalRowsSmem::BARS + CR_MAX_WARPS * 16 <= CalRowsSmem::WARP0, "tables and barriers share the first 2 KB");
+
+// counts of one step's 64 bytes (four 16-byte pieces in qv), bytes >= `lim` masked away: acc[v] += 0x80 per byte >= v
+template <int S, bool MASKED>
+__device__ __forceinline__ void cr_count(const uint4 (&qv)[4], int lim, uint32_t (&acc)[S]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {qv[k].x, qv[k].y, qv[k].z, qv[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t bm = 0x80808080u;
+            if (MASKED) {
+                const int r = min(max(lim - (16 * k + 4 * j), 0), 4);          // bytes of this word before the boundary (uniform)
+                bm = r == 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * r)) - 1u));
+            }
+            const uint32_t lo7 = w[j] & 0x7F7F7F7Fu;
+#pragma unroll
+            for (int v = 1; v < S; ++v) {
+                const uint32_t t = lo7 + (uint32_t)(0x80 - v) * 0x01010101u;
+                const uint32_t m = (t | w[j]) & bm;
+                asm("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(acc[v]) : "r"(m), "r"(0x01010101u));
+            }
+        }
+    }
+}
+
+// finish (channel c, history length h): gc / ge = #{x >= v} before the cutoff / the window end (index v = 1..S-1)
+template <int S>
+__device__ __forceinline__ void cr_finish(const CalibParams& P, const CalOut& O, const uint8_t* s_len, const uint8_t* s_rank, int K, int c, int h,
+                                          int cut, int end_out, int npost, bool has_post, const int (&gc)[S], const int (&ge)[S]) {
+    int hist[S], post[S];
+    {
+        int g_prev = cut, p_prev = has_post ? npost : 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int g_next = s + 1 < S ? gc[s + 1] : 0;
+            const int p_next = (has_post && s + 1 < S) ? ge[s + 1] - gc[s + 1] : 0;
+            hist[s] = g_prev - g_next;
+            post[s] = p_prev - p_next;
+            g_prev = g_next;
+            p_prev = p_next;
+        }
+    }
+    int p = 0;
+    if (P.use_sort) {   // np.argmax: lowest index on ties (functions_1.py:77)
+        int best = hist[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s)
+            if (hist[s] > best) { best = hist[s]; p = s; }
+    }
+    const uint4 rk4 = *reinterpret_cast<const uint4*>(s_rank + 16 * p);   // rank[p][s], s = 0..15
+    uint32_t rk[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t wsel = s < 4 ? rk4.x : (s < 8 ? rk4.y : rk4.z);
+        rk[s] = (wsel >> (8 * (s & 3))) & 0xFFu;
+    }
+    // byte rk[s] of a 16-byte length row (ranks < 8 live in the first two words: one data-dependent PRMT)
+    auto len_of = [&](const uint4& row, int s) -> uint32_t {
+        if (S <= 8) return __byte_perm(row.x, row.y, rk[s]) & 0xFFu;
+        return (rk[s] < 8 ? __byte_perm(row.x, row.y, rk[s]) : __byte_perm(row.z, row.w, rk[s] - 8)) & 0xFFu;
+    };
+    uint32_t best_cost = 0;
+    int enc = -1;
+    for (int k = 0; k < K; ++k) {   // np.argmin: first minimum (get_BR_no_sort.py:236); rows short: costs fit 32 bits
+        if (!((O.active >> k) & 1ull)) continue;
+        const uint4 row = *reinterpret_cast<const uint4*>(s_len + 16 * k);
+        uint32_t cost = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) cost += (uint32_t)hist[s] * len_of(row, s);
+        if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
+    }
+    if (enc < 0) enc = 0;
+    const uint4 erow = *reinterpret_cast<const uint4*>(s_len + 16 * enc);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) bits += (uint32_t)post[s] * len_of(erow, s);
+    const size_t o = (size_t)c * P.nH + h;
+    if (O.cutoff) O.cutoff[o] = cut;
+    if (O.end) O.end[o] = end_out;
+    if (O.peak) O.peak[o] = (uint8_t)p;
+    if (O.enc) O.enc[o] = (uint8_t)enc;
+    if (O.bits) O.bits[o] = (long long)bits;
+    if (O.nsym) O.nsym[o] = has_post ? (long long)npost : 0ll;
+    if (O.assign_m) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) O.assign_m[o * S + rk[s]] = hist[s];
+    }
+    if (O.post_m) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) O.post_m[o * S + rk[s]] = post[s];
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(CR_MAX_WARPS * 32, 1) k_calibrate_rows(const __grid_constant__ CalRowsParams PR) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    using SM = CalRowsSmem;
+    const CalibParams& P = PR.C;
+    const CalOut& O = P.out[0];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const uint4* gl = reinterpret_cast<const uint4*>(&O.tab->lens[0][0]);
+        const uint4* gr = reinterpret_cast<const uint4*>(&O.tab->rank[0][0]);
+        for (int i = threadIdx.x; i < MUA_MAX_K; i += blockDim.x) reinterpret_cast<uint4*>(smem_raw + SM::LEN)[i] = gl[i];
+        if (threadIdx.x < MUA_MAX_S) reinterpret_cast<uint4*>(smem_raw + SM::RANK)[threadIdx.x] = gr[threadIdx.x];
+    }
+    uint8_t* sm = smem_raw + SM::WARP0 + (size_t)warp * PR.per_warp;
+    const uint32_t in0 = smem_u32(sm);
+    const uint32_t in_lane = (in0 + lane * 128) | ((lane & 7) * 16);
+    uint16_t* snap = reinterpret_cast<uint16_t*>(sm + SM::SNAP) + lane;        // [h][v - 1][32 lanes]
+    const uint32_t bar0 = smem_u32(smem_raw + SM::BARS) + warp * 16;
+    if (lane == 0) {
+        mbar_init(reinterpret_cast<uint64_t*>(smem_raw + SM::BARS) + 2 * warp, 1);
+        mbar_init(reinterpret_cast<uint64_t*>(smem_raw + SM::BARS) + 2 * warp + 1, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const uint8_t* s_len = smem_raw + SM::LEN;
+    const uint8_t* s_rank = smem_raw + SM::RANK;
+    const int K = O.tab->K;
+    const int nblk = (P.L.C + 31) >> 5;
+    const int nev = PR.nev;
+    const int scan_end = nev > 0 ? PR.ev_pos[nev - 1] : 0;
+    const int nt = (scan_end + ER_TILE - 1) / ER_TILE, nbox = (nt + 1) >> 1;
+    uint32_t phase = 0;
+    if (warp >= PR.wuse) return;
+
+    for (int blk = blockIdx.x + gridDim.x * warp; blk < nblk; blk += gridDim.x * PR.wuse) {
+        const int c = blk * 32 + lane;
+        const bool valid = c < P.L.C;
+        auto issue_box = [&](int tt, uint32_t s, uint32_t dep) {
+            mbar_expect_tx_s(bar0 + 8 * s, SM::STAGE);
+            tma_load_2d(in0 + s * SM::STAGE, &PR.tmap, 128 * tt + (int)dep, blk * 32, bar0 + 8 * s);
+        };
+        if (lane == 0) {
+            if (nbox > 0) issue_box(0, 0, 0u);
+            if (nbox > 1) issue_box(1, 1, 0u);
+        }
+        uint32_t acc[S];
+#pragma unroll
+        for (int v = 0; v < S; ++v) acc[v] = 0;
+        int ev = 0;
+        // an event at a position the scan has reached: `g` = the lane's counts there
+        auto on_event = [&](int e, const uint32_t (&g)[S]) {
+            const int h = PR.ev_h[e], kind = PR.ev_kind[e];
+            if (kind == CR_EV_STORE) {
+#pragma unroll
+                for (int v = 1; v < S; ++v) snap[(h * (S - 1) + (v - 1)) * 32] = (uint16_t)(g[v] >> 7);
+            } else if (valid) {
+                int gc[S], ge[S];
+                gc[0] = ge[0] = 0;
+                if (kind == CR_EV_END) {
+#pragma unroll
+                    for (int v = 1; v < S; ++v) { gc[v] = snap[(h * (S - 1) + (v - 1)) * 32]; ge[v] = (int)(g[v] >> 7); }
+                    cr_finish<S>(P, O, s_len, s_rank, K, c, h, PR.cutv[h], PR.endv[h], PR.endv[h] - PR.cutv[h], true, gc, ge);
+                } else {
+#pragma unroll
+                    for (int v = 1; v < S; ++v) { gc[v] = (int)(g[v] >> 7); ge[v] = 0; }
+                    cr_finish<S>(P, O, s_len, s_rank, K, c, h, PR.cutv[h], PR.endv[h], 0, false, gc, ge);
+                }
+            }
+        };
+        int ts = 0;
+        for (int t = 0; t < nt; ++t, ts += ER_TILE) {
+            const uint32_t s = (t >> 1) & 1u;
+            if ((t & 1) == 0) {
+                mbar_wait_s(bar0 + 8 * s, (phase >> s) & 1u);
+                phase ^= 1u << s;
+            }
+            const uint32_t tile = (in_lane + s * SM::STAGE) ^ ((t & 1) * 64u);
+            uint4 qv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) qv[k] = lds_u128(tile ^ (16u * k));
+            if ((t & 1) && (t >> 1) + 2 < nbox) {   // the box is in registers: its stage takes the box after the next one
+                const uint32_t dep = (qv[0].x | qv[1].x | qv[2].x | qv[3].x) & PR.zero;   // the four loads have been performed
+                __syncwarp();
+                if (lane == 0) issue_box((t >> 1) + 2, (t >> 1) & 1u, dep);
+            }
+            while (ev < nev && PR.ev_pos[ev] < ts + ER_TILE) {   // boundaries inside the step: masked recount
+                uint32_t g[S];
+#pragma unroll
+                for (int v = 0; v < S; ++v) g[v] = acc[v];
+                cr_count<S, true>(qv, PR.ev_pos[ev] - ts, g);
+                on_event(ev, g);
+                ++ev;
+            }
+            cr_count<S, false>(qv, 0, acc);
+            while (ev < nev && PR.ev_pos[ev] == ts + ER_TILE) {  // boundaries at the end of the step
+                on_event(ev, acc);
+                ++ev;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace mua

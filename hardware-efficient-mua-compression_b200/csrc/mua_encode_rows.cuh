@@ -52,6 +52,7 @@ static_assert(ER_LUT_MAX + ER_WARPS * 16 <= EncRowsSmem::WARP0, "tables and barr
 struct EncRowsParams {
     EncParams E;
     int32_t wuse;                       // warps of a CTA that take blocks
+    uint32_t zero;                      // == 0, opaque to the compiler: ties a TMA request to the registers loaded from the stage it refills
     alignas(64) CUtensorMap tmap;       // FIXED: uint8 [C][stride] as a 2-D tensor (T bins x C channels), box 128 x 32, 128-byte swizzle
 };
 
@@ -186,15 +187,19 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows(const __grid_c
                 for (int i = 0; i < (FIXED ? 0 : 4); ++i)
                     if (t * ER_TILE < lim_i[FIXED ? 0 : i]) cp_async16(dst_l + s * SM::STAGE + i * (8 * ER_ROWB), src_i[FIXED ? 0 : i] + t * ER_TILE);
             };
-            auto issue_box = [&](int tt, uint32_t s) {   // FIXED: request box tt (steps 2 tt and 2 tt + 1) into stage s; lane 0 only
+            // FIXED: request box tt (steps 2 tt and 2 tt + 1) into stage s; lane 0 only.  `dep` (== 0) is computed from the registers
+            // the stage's last reads filled: a warp-wide LDS retires as a whole, so the request cannot be issued before EVERY lane's
+            // reads of the stage have been performed (a __syncwarp alone only orders their issue, and with ~20 warps queueing
+            // shared-memory loads an L2-hit box can land before a queued load executes)
+            auto issue_box = [&](int tt, uint32_t s, uint32_t dep) {
                 mbar_expect_tx_s(bar0 + 8 * s, SM::STAGE);
-                tma_load_2d(in0 + s * SM::STAGE, &PR.tmap, tlo + 128 * tt, blk * 32, bar0 + 8 * s);
+                tma_load_2d(in0 + s * SM::STAGE, &PR.tmap, tlo + 128 * tt + (int)dep, blk * 32, bar0 + 8 * s);
             };
             const int nbox = (nt + 1) >> 1;
             if (FIXED) {
                 if (lane == 0) {
-                    issue_box(0, 0);
-                    if (nbox > 1) issue_box(1, 1);
+                    issue_box(0, 0, 0u);
+                    if (nbox > 1) issue_box(1, 1, 0u);
                 }
             } else {
                 issue(0, 0);
@@ -226,8 +231,9 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows(const __grid_c
                     any_hi |= (qv[k].x | qv[k].y) | (qv[k].z | qv[k].w);
                 }
                 if (FIXED && (t & 1) && (t >> 1) + 2 < nbox) {   // the box is in registers: its stage takes the box after the next one
+                    const uint32_t dep = any_hi & PR.zero;
                     __syncwarp();
-                    if (lane == 0) issue_box((t >> 1) + 2, (t >> 1) & 1u);
+                    if (lane == 0) issue_box((t >> 1) + 2, (t >> 1) & 1u, dep);
                 }
                 if (any_hi & 0x80808080u) {   // rare: a count >= 128 (or stale bytes of a row that ended)
 #pragma unroll

@@ -41,3 +41,16 @@ def recordings():
 def sclv_tables():
     from oracle import mua_oracle
     return mua_oracle.load_sclv_tables()
+
+
+@pytest.fixture(params=["lanes", "warps"])
+def kernel_family(request):
+    """Short rows have two kernel families behind the same ABI calls: a lane per channel (k_encode_rows, k_calibrate_rows; picked
+    for recordings of many short rows) and a warp per channel.  MUA_ROWS_MIN_C is read by the library at every call."""
+    old = os.environ.get("MUA_ROWS_MIN_C")
+    os.environ["MUA_ROWS_MIN_C"] = "0" if request.param == "lanes" else "2147483647"
+    yield request.param
+    if old is None:
+        os.environ.pop("MUA_ROWS_MIN_C", None)
+    else:
+        os.environ["MUA_ROWS_MIN_C"] = old

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_family")]   # every test runs with the lane-per-channel and the warp-per-channel kernels
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -7,7 +7,7 @@ import torch
 
 from oracle import mua_oracle as O
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_family")]   # every test runs with the lane-per-channel and the warp-per-channel kernels
 
 import mua_b200  # noqa: E402
 from mua_b200 import pipeline as P, io as mio, _lib  # noqa: E402

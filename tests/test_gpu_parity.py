@@ -8,7 +8,7 @@ import torch
 from conftest import load_golden
 from oracle import mua_oracle as O
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_family")]   # every test runs with the lane-per-channel and the warp-per-channel kernels
 
 import mua_b200  # noqa: E402
 from mua_b200 import drivers, pipeline as P  # noqa: E402

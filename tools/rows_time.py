@@ -17,7 +17,7 @@ def timeit(fn, n=20):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for BP in (50, 10, 1):
+for BP in [int(b) for b in os.environ.get('ROWS_BPS', '50,10,1').split(',')]:
     T = 120000 // BP
     thr = P.synth_threshold_table(float(BP))
     rec = P.synth_recording(C, T, seed=5, BP_ms=float(BP), bursty=True, device="cuda", thr=thr)
