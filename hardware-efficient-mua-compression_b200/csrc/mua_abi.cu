@@ -141,8 +141,8 @@ int launch_calibrate_rows(const CalibParams& P, cudaStream_t st) {
     memset(&PR, 0, sizeof(PR));
     PR.C = P;
     const int T = P.L.T, nH = P.nH;
-    // the boundaries of every channel (all rows are T bins long), sorted: cutoffs that a post window follows keep their counts
-    struct Ev { int pos, kind, h; } ev[2 * MUA_MAX_H];
+    // the boundaries of every channel (all rows are T bins long), sorted by position
+    struct Ev { int pos, h, is_end; } ev[2 * MUA_MAX_H];
     int nev = 0;
     for (int h = 0; h < nH; ++h) {
         const int cut = T < (P.H[h] > 1 ? P.H[h] : 1) ? T : (P.H[h] > 1 ? P.H[h] : 1);   // functions_1.py:59-68
@@ -156,22 +156,24 @@ int launch_calibrate_rows(const CalibParams& P, cudaStream_t st) {
         const bool has_post = end > 0 && P.mode != MUA_WINDOW_NONE && P.need_post;
         PR.cutv[h] = cut;
         PR.endv[h] = P.mode == MUA_WINDOW_NONE ? cut : end;
-        if (has_post) {
-            ev[nev++] = Ev{cut, CR_EV_STORE, h};
-            ev[nev++] = Ev{end, CR_EV_END, h};
-        } else {
-            ev[nev++] = Ev{cut, CR_EV_CUT_ONLY, h};
-        }
+        ev[nev++] = Ev{cut, h, 0};
+        if (has_post) ev[nev++] = Ev{end, h, 1};
     }
-    for (int i = 1; i < nev; ++i)   // insertion sort by (position, kind)
-        for (int j = i; j > 0 && (ev[j].pos < ev[j - 1].pos || (ev[j].pos == ev[j - 1].pos && ev[j].kind < ev[j - 1].kind)); --j) {
+    for (int i = 1; i < nev; ++i)   // insertion sort
+        for (int j = i; j > 0 && ev[j].pos < ev[j - 1].pos; --j) {
             const Ev t = ev[j]; ev[j] = ev[j - 1]; ev[j - 1] = t;
         }
     PR.nev = nev;
-    for (int i = 0; i < nev; ++i) { PR.ev_pos[i] = ev[i].pos; PR.ev_kind[i] = (uint8_t)ev[i].kind; PR.ev_h[i] = (uint8_t)ev[i].h; }
-    PR.per_warp = 2 * CalRowsSmem::STAGE + ((nH * (S - 1) * 64 + 1023) / 1024) * 1024;
-    int warps = (227 * 1024 - CalRowsSmem::WARP0) / PR.per_warp;
-    if (warps > CR_MAX_WARPS) warps = CR_MAX_WARPS;
+    for (int h = 0; h < MUA_MAX_H; ++h) PR.ev_cut[h] = 0, PR.ev_end[h] = -1;
+    for (int i = 0; i < nev; ++i) {
+        PR.ev_pos[i] = ev[i].pos;
+        if (ev[i].is_end) PR.ev_end[ev[i].h] = i; else PR.ev_cut[ev[i].h] = i;
+    }
+    PR.snap_bytes = nev * (S - 1) * 64;
+    int warps = (227 * 1024 - CalRowsSmem::TAIL) / (2 * CalRowsSmem::STAGE + PR.snap_bytes);
+    if (warps > cr_max_warps(S)) warps = cr_max_warps(S);
+    REQUIRE(warps >= 1, "calibrate: too many boundaries for shared memory");
+    PR.warps = warps;
     const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)P.L.C};
     const cuuint64_t gstr[1] = {(cuuint64_t)P.L.stride};
     const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
@@ -183,7 +185,7 @@ int launch_calibrate_rows(const CalibParams& P, cudaStream_t st) {
     const int grid = (int)(nblk < sm_count() ? nblk : sm_count());
     const long long per_sm = (nblk + grid - 1) / grid, rounds = (per_sm + warps - 1) / warps;
     PR.wuse = (int32_t)((per_sm + rounds - 1) / rounds);
-    const int smem = CalRowsSmem::WARP0 + warps * PR.per_warp;
+    const int smem = warps * (2 * CalRowsSmem::STAGE + PR.snap_bytes) + CalRowsSmem::TAIL;
     cudaError_t e = cudaFuncSetAttribute(k_calibrate_rows<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "calibrate smem attribute");
     k_calibrate_rows<S><<<grid, warps * 32, smem, st>>>(PR);

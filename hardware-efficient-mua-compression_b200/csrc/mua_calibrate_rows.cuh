@@ -9,11 +9,12 @@
 //   * every lane keeps the cumulative counts #{x >= v} (v = 1..S-1) of ITS channel in registers: per 4 bytes and threshold
 //     one add, one LOP3 and one DP4A (the SWAR threshold compare of k_calibrate), no cross-lane traffic at all;
 //   * the boundaries are a host-sorted list of warp-uniform events.  A boundary inside a 64-bin step costs one masked
-//     recount of that step (same three instructions per word, byte mask from the uniform datapath); a cutoff stores the
-//     lane's counts as uint16 in its own shared-memory column, a window end (or a cutoff without post window) finishes
-//     (channel, history length) on the spot: histograms as count differences, first argmax, SCLV costs with the rank map
-//     applied by a data-dependent PRMT on the 16-byte length row (one PRMT + one IMAD per row and symbol), first argmin, bit
-//     count -- the epilogue of k_calibrate, one lane per channel.
+//     recount of that step (same three instructions per word, byte mask from the uniform datapath); every boundary
+//     stores the lane's counts as uint16 in its own shared-memory column;
+//   * after the scan the warp's 32 x nH (channel, history length) pairs are finished one per lane in OUTPUT order, so every
+//     [C][nH] result array is written with fully coalesced stores (a lane per channel would scatter 4-byte stores nH elements
+//     apart): histograms as count differences, first argmax, SCLV costs with the rank map applied by a data-dependent PRMT on
+//     the 16-byte length row (one PRMT + one IMAD per row and symbol), first argmin, bit count -- the epilogue of k_calibrate.
 // Results are those of k_calibrate (same oracle, same tests; every GPU test runs with both kernel families).
 #pragma once
 #include <cuda.h>
@@ -24,37 +25,37 @@
 namespace mua {
 
 constexpr int CR_MAX_WARPS = 24;
-constexpr int CR_EV_STORE = 0;      // cutoff followed by a post window: keep the counts
-constexpr int CR_EV_END = 1;        // window end: finish (channel, h) with the kept counts
-constexpr int CR_EV_CUT_ONLY = 2;   // cutoff without post window (window NONE / skipped channel / post outputs not wanted)
+// warps per CTA: the kept counts of S > 3 leave room for fewer than 17 warps anyway, and 512 threads may use 128 registers
+__host__ __device__ constexpr int cr_max_warps(int S) { return S <= 3 ? CR_MAX_WARPS : 16; }
 
 struct CalRowsParams {
     CalibParams C;
     int32_t wuse;                        // warps of a CTA that take blocks
     uint32_t zero;                       // == 0, opaque to the compiler (see k_encode_rows: ties a TMA request to the stage's last reads)
-    int32_t nev;                         // events, sorted by position (stores before ends at equal positions)
+    int32_t nev;                         // boundaries (cutoffs and window ends of all history lengths), sorted by position
     int32_t ev_pos[2 * MUA_MAX_H];
-    uint8_t ev_kind[2 * MUA_MAX_H], ev_h[2 * MUA_MAX_H];
-    int32_t cutv[MUA_MAX_H], endv[MUA_MAX_H];   // what d_cutoff / d_end receive
-    int32_t per_warp;                    // shared-memory bytes per warp: two stages + the kept counts
+    int32_t cutv[MUA_MAX_H], endv[MUA_MAX_H];       // what d_cutoff / d_end receive
+    int32_t ev_cut[MUA_MAX_H], ev_end[MUA_MAX_H];   // boundary index of the cutoff / the window end (-1: no post window)
+    int32_t warps;                       // warps per CTA; shared memory: [warps x 2 stages][warps x counts][tables]
+    int32_t snap_bytes;                  // counts kept per warp: uint16 [nev][S - 1][32 lanes]
     alignas(64) CUtensorMap tmap;
 };
 
-struct CalRowsSmem {
+struct CalRowsSmem {                     // after the stages and the kept counts of all warps:
+    static constexpr int STAGE = 4096;
     static constexpr int LEN = 0;                        // MUA_MAX_K x 16 B SCLV rows
     static constexpr int RANK = LEN + MUA_MAX_K * 16;    // MUA_MAX_S x 16 B rank maps
-    static constexpr int BARS = RANK + MUA_MAX_S * 16;   // 2 mbarriers per warp
-    static constexpr int WARP0 = 2048;
-    static constexpr int STAGE = 4096;
-    static constexpr int SNAP = 2 * STAGE;               // uint16 [nH][S - 1][32 lanes]
+    static constexpr int HINFO = RANK + MUA_MAX_S * 16;  // int32 [4][MUA_MAX_H]: cutv, endv, ev_cut, ev_end
+    static constexpr int BARS = HINFO + 4 * MUA_MAX_H * 4;   // 2 mbarriers per warp
+    static constexpr int TAIL = BARS + CR_MAX_WARPS * 16;
 };
-static_assert(CalRowsSmem::BARS + CR_MAX_WARPS * 16 <= CalRowsSmem::WARP0, "tables and barriers share the first 2 KB");
 
 // counts of one step's 64 bytes (four 16-byte pieces in qv), bytes >= `lim` masked away: acc[v] += 0x80 per byte >= v
 template <int S, bool MASKED>
 __device__ __forceinline__ void cr_count(const uint4 (&qv)[4], int lim, uint32_t (&acc)[S]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        if (MASKED && lim <= 16 * k) break;                                     // pieces past the boundary (uniform branch)
         const uint32_t w[4] = {qv[k].x, qv[k].y, qv[k].z, qv[k].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -143,32 +144,41 @@ __device__ __forceinline__ void cr_finish(const CalibParams& P, const CalOut& O,
 }
 
 template <int S>
-__global__ void __launch_bounds__(CR_MAX_WARPS * 32, 1) k_calibrate_rows(const __grid_constant__ CalRowsParams PR) {
+__global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(const __grid_constant__ CalRowsParams PR) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = CalRowsSmem;
     const CalibParams& P = PR.C;
     const CalOut& O = P.out[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* tail = smem_raw + (size_t)PR.warps * (2 * SM::STAGE + PR.snap_bytes);
     {
         const uint4* gl = reinterpret_cast<const uint4*>(&O.tab->lens[0][0]);
         const uint4* gr = reinterpret_cast<const uint4*>(&O.tab->rank[0][0]);
-        for (int i = threadIdx.x; i < MUA_MAX_K; i += blockDim.x) reinterpret_cast<uint4*>(smem_raw + SM::LEN)[i] = gl[i];
-        if (threadIdx.x < MUA_MAX_S) reinterpret_cast<uint4*>(smem_raw + SM::RANK)[threadIdx.x] = gr[threadIdx.x];
+        for (int i = threadIdx.x; i < MUA_MAX_K; i += blockDim.x) reinterpret_cast<uint4*>(tail + SM::LEN)[i] = gl[i];
+        if (threadIdx.x < MUA_MAX_S) reinterpret_cast<uint4*>(tail + SM::RANK)[threadIdx.x] = gr[threadIdx.x];
+        if (threadIdx.x < MUA_MAX_H) {
+            int32_t* hi = reinterpret_cast<int32_t*>(tail + SM::HINFO);
+            hi[threadIdx.x] = PR.cutv[threadIdx.x];
+            hi[MUA_MAX_H + threadIdx.x] = PR.endv[threadIdx.x];
+            hi[2 * MUA_MAX_H + threadIdx.x] = PR.ev_cut[threadIdx.x];
+            hi[3 * MUA_MAX_H + threadIdx.x] = PR.ev_end[threadIdx.x];
+        }
     }
-    uint8_t* sm = smem_raw + SM::WARP0 + (size_t)warp * PR.per_warp;
-    const uint32_t in0 = smem_u32(sm);
+    const uint32_t in0 = smem_u32(smem_raw) + warp * (2 * SM::STAGE);
     const uint32_t in_lane = (in0 + lane * 128) | ((lane & 7) * 16);
-    uint16_t* snap = reinterpret_cast<uint16_t*>(sm + SM::SNAP) + lane;        // [h][v - 1][32 lanes]
-    const uint32_t bar0 = smem_u32(smem_raw + SM::BARS) + warp * 16;
+    uint16_t* snap = reinterpret_cast<uint16_t*>(smem_raw + (size_t)PR.warps * (2 * SM::STAGE) + (size_t)warp * PR.snap_bytes);   // [e][v - 1][32 lanes]
+    const uint32_t bar0 = smem_u32(tail + SM::BARS) + warp * 16;
     if (lane == 0) {
-        mbar_init(reinterpret_cast<uint64_t*>(smem_raw + SM::BARS) + 2 * warp, 1);
-        mbar_init(reinterpret_cast<uint64_t*>(smem_raw + SM::BARS) + 2 * warp + 1, 1);
+        mbar_init(reinterpret_cast<uint64_t*>(tail + SM::BARS) + 2 * warp, 1);
+        mbar_init(reinterpret_cast<uint64_t*>(tail + SM::BARS) + 2 * warp + 1, 1);
         fence_barrier_init();
     }
     __syncthreads();
-    const uint8_t* s_len = smem_raw + SM::LEN;
-    const uint8_t* s_rank = smem_raw + SM::RANK;
+    const uint8_t* s_len = tail + SM::LEN;
+    const uint8_t* s_rank = tail + SM::RANK;
+    const int32_t* s_hinfo = reinterpret_cast<const int32_t*>(tail + SM::HINFO);
     const int K = O.tab->K;
+    const int nH = P.nH;
     const int nblk = (P.L.C + 31) >> 5;
     const int nev = PR.nev;
     const int scan_end = nev > 0 ? PR.ev_pos[nev - 1] : 0;
@@ -177,8 +187,6 @@ __global__ void __launch_bounds__(CR_MAX_WARPS * 32, 1) k_calibrate_rows(const _
     if (warp >= PR.wuse) return;
 
     for (int blk = blockIdx.x + gridDim.x * warp; blk < nblk; blk += gridDim.x * PR.wuse) {
-        const int c = blk * 32 + lane;
-        const bool valid = c < P.L.C;
         auto issue_box = [&](int tt, uint32_t s, uint32_t dep) {
             mbar_expect_tx_s(bar0 + 8 * s, SM::STAGE);
             tma_load_2d(in0 + s * SM::STAGE, &PR.tmap, 128 * tt + (int)dep, blk * 32, bar0 + 8 * s);
@@ -187,29 +195,14 @@ __global__ void __launch_bounds__(CR_MAX_WARPS * 32, 1) k_calibrate_rows(const _
             if (nbox > 0) issue_box(0, 0, 0u);
             if (nbox > 1) issue_box(1, 1, 0u);
         }
+        // ---- scan: the lane's cumulative counts, kept at every boundary ----
         uint32_t acc[S];
 #pragma unroll
         for (int v = 0; v < S; ++v) acc[v] = 0;
         int ev = 0;
-        // an event at a position the scan has reached: `g` = the lane's counts there
-        auto on_event = [&](int e, const uint32_t (&g)[S]) {
-            const int h = PR.ev_h[e], kind = PR.ev_kind[e];
-            if (kind == CR_EV_STORE) {
+        auto keep = [&](int e, const uint32_t (&g)[S]) {
 #pragma unroll
-                for (int v = 1; v < S; ++v) snap[(h * (S - 1) + (v - 1)) * 32] = (uint16_t)(g[v] >> 7);
-            } else if (valid) {
-                int gc[S], ge[S];
-                gc[0] = ge[0] = 0;
-                if (kind == CR_EV_END) {
-#pragma unroll
-                    for (int v = 1; v < S; ++v) { gc[v] = snap[(h * (S - 1) + (v - 1)) * 32]; ge[v] = (int)(g[v] >> 7); }
-                    cr_finish<S>(P, O, s_len, s_rank, K, c, h, PR.cutv[h], PR.endv[h], PR.endv[h] - PR.cutv[h], true, gc, ge);
-                } else {
-#pragma unroll
-                    for (int v = 1; v < S; ++v) { gc[v] = (int)(g[v] >> 7); ge[v] = 0; }
-                    cr_finish<S>(P, O, s_len, s_rank, K, c, h, PR.cutv[h], PR.endv[h], 0, false, gc, ge);
-                }
-            }
+            for (int v = 1; v < S; ++v) snap[(e * (S - 1) + (v - 1)) * 32 + lane] = (uint16_t)(g[v] >> 7);
         };
         int ts = 0;
         for (int t = 0; t < nt; ++t, ts += ER_TILE) {
@@ -232,14 +225,29 @@ __global__ void __launch_bounds__(CR_MAX_WARPS * 32, 1) k_calibrate_rows(const _
 #pragma unroll
                 for (int v = 0; v < S; ++v) g[v] = acc[v];
                 cr_count<S, true>(qv, PR.ev_pos[ev] - ts, g);
-                on_event(ev, g);
+                keep(ev, g);
                 ++ev;
             }
             cr_count<S, false>(qv, 0, acc);
             while (ev < nev && PR.ev_pos[ev] == ts + ER_TILE) {  // boundaries at the end of the step
-                on_event(ev, acc);
+                keep(ev, acc);
                 ++ev;
             }
+        }
+        __syncwarp();
+        // ---- (channel, history length) pairs in output order, one per lane ----
+        const int npair = min(32, P.L.C - blk * 32) * nH;
+        for (int it = lane; it < npair; it += 32) {
+            const int cl = it / nH, h = it - cl * nH;
+            const int cut = s_hinfo[h], end_out = s_hinfo[MUA_MAX_H + h], ec = s_hinfo[2 * MUA_MAX_H + h], ee = s_hinfo[3 * MUA_MAX_H + h];
+            int gc[S], ge[S];
+            gc[0] = ge[0] = 0;
+#pragma unroll
+            for (int v = 1; v < S; ++v) {
+                gc[v] = snap[(ec * (S - 1) + (v - 1)) * 32 + cl];
+                ge[v] = ee >= 0 ? snap[(ee * (S - 1) + (v - 1)) * 32 + cl] : 0;
+            }
+            cr_finish<S>(P, O, s_len, s_rank, K, blk * 32 + cl, h, cut, end_out, ee >= 0 ? end_out - cut : 0, ee >= 0, gc, ge);
         }
         __syncwarp();
     }
