@@ -170,22 +170,24 @@ int launch_calibrate_rows(const CalibParams& P, cudaStream_t st) {
         if (ev[i].is_end) PR.ev_end[ev[i].h] = i; else PR.ev_cut[ev[i].h] = i;
     }
     PR.snap_bytes = nev * (S - 1) * 64;
-    int warps = (227 * 1024 - CalRowsSmem::TAIL) / (2 * CalRowsSmem::STAGE + PR.snap_bytes);
+    constexpr int stage = cr_box(S) * 32;
+    int warps = (227 * 1024 - CalRowsSmem::TAIL) / (2 * stage + PR.snap_bytes);
     if (warps > cr_max_warps(S)) warps = cr_max_warps(S);
     REQUIRE(warps >= 1, "calibrate: too many boundaries for shared memory");
     PR.warps = warps;
     const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)P.L.C};
     const cuuint64_t gstr[1] = {(cuuint64_t)P.L.stride};
-    const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {(cuuint32_t)cr_box(S), 32}, estr[2] = {1, 1};
     const CUresult r = tensor_map_encoder()(&PR.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(P.L.sym), gdim, gstr, box, estr,
-                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, cr_box(S) == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     const long long nblk = ((long long)P.L.C + 31) / 32;
     const int grid = (int)(nblk < sm_count() ? nblk : sm_count());
     const long long per_sm = (nblk + grid - 1) / grid, rounds = (per_sm + warps - 1) / warps;
     PR.wuse = (int32_t)((per_sm + rounds - 1) / rounds);
-    const int smem = warps * (2 * CalRowsSmem::STAGE + PR.snap_bytes) + CalRowsSmem::TAIL;
+    const int smem = warps * (2 * stage + PR.snap_bytes) + CalRowsSmem::TAIL;
     cudaError_t e = cudaFuncSetAttribute(k_calibrate_rows<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "calibrate smem attribute");
     k_calibrate_rows<S><<<grid, warps * 32, smem, st>>>(PR);
@@ -666,6 +668,45 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         if (S == 2) MUA_LAUNCH_ENC(2);
         else MUA_LAUNCH_ENC(3);
 #undef MUA_LAUNCH_ENC
+    } else if (h.Lmax <= 8 && S >= 3 && S <= 9 && T > 0 && T <= rows_t_max() && C >= rows_min_channels() && !d_off && !d_len &&
+               tensor_map_encoder() != nullptr && (227 * 1024 - S * K * 512) / (2 * ERP_STAGE + ERP_RING + 16) >= 8) {
+        // many short rows, pair-table codebooks: a lane per channel (k_encode_rows_pair), all pair tables in shared memory
+        EncRowsPairParams PR;
+        PR.E = P;
+        PR.zero = 0;
+        PR.lut_bytes = S * K * 512;
+        int warps = (227 * 1024 - PR.lut_bytes) / (2 * ERP_STAGE + ERP_RING + 16);
+        if (warps > ER_WARPS) warps = ER_WARPS;
+        PR.warps = warps;
+        memset(&PR.tmap, 0, sizeof(PR.tmap));
+        const cuuint64_t gdim[2] = {(cuuint64_t)T, (cuuint64_t)C};
+        const cuuint64_t gstr[1] = {(cuuint64_t)stride};
+        const cuuint32_t box[2] = {ER_TILE, 32}, estr[2] = {1, 1};
+        const CUresult r = tensor_map_encoder()(&PR.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(d_sym), gdim, gstr, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        const long long nblk = ((long long)C + 31) / 32;
+        const int grid = (int)(nblk < sm_count() ? nblk : sm_count());
+        const long long per_sm = (nblk + grid - 1) / grid, rounds = (per_sm + warps - 1) / warps;
+        PR.wuse = (int32_t)((per_sm + rounds - 1) / rounds);
+        const int smem = warps * (2 * ERP_STAGE + ERP_RING + 16) + PR.lut_bytes;
+#define MUA_LAUNCH_ENCRP(SV)                                                                                            \
+    do {                                                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(k_encode_rows_pair<SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                            \
+        k_encode_rows_pair<SV><<<grid, warps * 32, smem, st>>>(PR);                                                     \
+    } while (0)
+        switch (S) {
+            case 3: MUA_LAUNCH_ENCRP(3); break;
+            case 4: MUA_LAUNCH_ENCRP(4); break;
+            case 5: MUA_LAUNCH_ENCRP(5); break;
+            case 6: MUA_LAUNCH_ENCRP(6); break;
+            case 7: MUA_LAUNCH_ENCRP(7); break;
+            case 8: MUA_LAUNCH_ENCRP(8); break;
+            default: MUA_LAUNCH_ENCRP(9); break;
+        }
+#undef MUA_LAUNCH_ENCRP
     } else if (h.Lmax <= 8 && S >= 3 && S <= 9) {
         const int smem = EncPairSmem::PER_WARP * ENC_WARPS;
         const int grid = ctas_needed < sm_count() * 3 ? ctas_needed : sm_count() * 3;

@@ -25,8 +25,12 @@
 namespace mua {
 
 constexpr int CR_MAX_WARPS = 24;
-// warps per CTA: the kept counts of S > 3 leave room for fewer than 17 warps anyway, and 512 threads may use 128 registers
-__host__ __device__ constexpr int cr_max_warps(int S) { return S <= 3 ? CR_MAX_WARPS : 16; }
+// warps per CTA: the kept counts of S > 6 leave room for fewer than 22 warps (what 100k channels ask for) anyway, and 512 threads
+// may use 128 registers
+__host__ __device__ constexpr int cr_max_warps(int S) { return S <= 6 ? CR_MAX_WARPS : 16; }
+// bins per TMA box: 128 (two steps, 128-byte swizzle) while the scan is memory-bound; S > 3 count more thresholds per byte and
+// keep more counts per boundary: half-size boxes (one step, 64-byte swizzle) leave shared memory for twice the warps
+__host__ __device__ constexpr int cr_box(int S) { return S <= 3 ? 128 : 64; }
 
 struct CalRowsParams {
     CalibParams C;
@@ -36,13 +40,12 @@ struct CalRowsParams {
     int32_t ev_pos[2 * MUA_MAX_H];
     int32_t cutv[MUA_MAX_H], endv[MUA_MAX_H];       // what d_cutoff / d_end receive
     int32_t ev_cut[MUA_MAX_H], ev_end[MUA_MAX_H];   // boundary index of the cutoff / the window end (-1: no post window)
-    int32_t warps;                       // warps per CTA; shared memory: [warps x 2 stages][warps x counts][tables]
+    int32_t warps;                       // warps per CTA; shared memory: [warps x 2 stages][warps x counts][tables]; a stage = one box
     int32_t snap_bytes;                  // counts kept per warp: uint16 [nev][S - 1][32 lanes]
     alignas(64) CUtensorMap tmap;
 };
 
 struct CalRowsSmem {                     // after the stages and the kept counts of all warps:
-    static constexpr int STAGE = 4096;
     static constexpr int LEN = 0;                        // MUA_MAX_K x 16 B SCLV rows
     static constexpr int RANK = LEN + MUA_MAX_K * 16;    // MUA_MAX_S x 16 B rank maps
     static constexpr int HINFO = RANK + MUA_MAX_S * 16;  // int32 [4][MUA_MAX_H]: cutv, endv, ev_cut, ev_end
@@ -149,8 +152,9 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
     using SM = CalRowsSmem;
     const CalibParams& P = PR.C;
     const CalOut& O = P.out[0];
+    constexpr int BOXW = cr_box(S), SPB = BOXW / ER_TILE, STAGE = BOXW * 32;   // steps per box, bytes per stage
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* tail = smem_raw + (size_t)PR.warps * (2 * SM::STAGE + PR.snap_bytes);
+    uint8_t* tail = smem_raw + (size_t)PR.warps * (2 * STAGE + PR.snap_bytes);
     {
         const uint4* gl = reinterpret_cast<const uint4*>(&O.tab->lens[0][0]);
         const uint4* gr = reinterpret_cast<const uint4*>(&O.tab->rank[0][0]);
@@ -164,9 +168,11 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
             hi[3 * MUA_MAX_H + threadIdx.x] = PR.ev_end[threadIdx.x];
         }
     }
-    const uint32_t in0 = smem_u32(smem_raw) + warp * (2 * SM::STAGE);
-    const uint32_t in_lane = (in0 + lane * 128) | ((lane & 7) * 16);
-    uint16_t* snap = reinterpret_cast<uint16_t*>(smem_raw + (size_t)PR.warps * (2 * SM::STAGE) + (size_t)warp * PR.snap_bytes);   // [e][v - 1][32 lanes]
+    const uint32_t in0 = smem_u32(smem_raw) + warp * (2 * STAGE);
+    // the lane's row of stage 0 with the swizzle of its pieces folded in: 128-byte rows, piece k at 16 (k ^ (l & 7)); 64-byte rows,
+    // piece k at 16 (k ^ ((l >> 1) & 3))
+    const uint32_t in_lane = BOXW == 128 ? (in0 + lane * 128) | ((lane & 7) * 16) : (in0 + lane * 64) | (((lane >> 1) & 3) * 16);
+    uint16_t* snap = reinterpret_cast<uint16_t*>(smem_raw + (size_t)PR.warps * (2 * STAGE) + (size_t)warp * PR.snap_bytes);   // [e][v - 1][32 lanes]
     const uint32_t bar0 = smem_u32(tail + SM::BARS) + warp * 16;
     if (lane == 0) {
         mbar_init(reinterpret_cast<uint64_t*>(tail + SM::BARS) + 2 * warp, 1);
@@ -182,14 +188,14 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
     const int nblk = (P.L.C + 31) >> 5;
     const int nev = PR.nev;
     const int scan_end = nev > 0 ? PR.ev_pos[nev - 1] : 0;
-    const int nt = (scan_end + ER_TILE - 1) / ER_TILE, nbox = (nt + 1) >> 1;
+    const int nt = (scan_end + ER_TILE - 1) / ER_TILE, nbox = (nt + SPB - 1) / SPB;
     uint32_t phase = 0;
     if (warp >= PR.wuse) return;
 
     for (int blk = blockIdx.x + gridDim.x * warp; blk < nblk; blk += gridDim.x * PR.wuse) {
         auto issue_box = [&](int tt, uint32_t s, uint32_t dep) {
-            mbar_expect_tx_s(bar0 + 8 * s, SM::STAGE);
-            tma_load_2d(in0 + s * SM::STAGE, &PR.tmap, 128 * tt + (int)dep, blk * 32, bar0 + 8 * s);
+            mbar_expect_tx_s(bar0 + 8 * s, STAGE);
+            tma_load_2d(in0 + s * STAGE, &PR.tmap, BOXW * tt + (int)dep, blk * 32, bar0 + 8 * s);
         };
         if (lane == 0) {
             if (nbox > 0) issue_box(0, 0, 0u);
@@ -206,19 +212,20 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
         };
         int ts = 0;
         for (int t = 0; t < nt; ++t, ts += ER_TILE) {
-            const uint32_t s = (t >> 1) & 1u;
-            if ((t & 1) == 0) {
+            const int bb = t / SPB, sub = t % SPB;   // box and step in the box
+            const uint32_t s = bb & 1u;
+            if (sub == 0) {
                 mbar_wait_s(bar0 + 8 * s, (phase >> s) & 1u);
                 phase ^= 1u << s;
             }
-            const uint32_t tile = (in_lane + s * SM::STAGE) ^ ((t & 1) * 64u);
+            const uint32_t tile = (in_lane + s * STAGE) ^ (sub * 64u);
             uint4 qv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) qv[k] = lds_u128(tile ^ (16u * k));
-            if ((t & 1) && (t >> 1) + 2 < nbox) {   // the box is in registers: its stage takes the box after the next one
+            if (sub == SPB - 1 && bb + 2 < nbox) {   // the box is in registers: its stage takes the box after the next one
                 const uint32_t dep = (qv[0].x | qv[1].x | qv[2].x | qv[3].x) & PR.zero;   // the four loads have been performed
                 __syncwarp();
-                if (lane == 0) issue_box((t >> 1) + 2, (t >> 1) & 1u, dep);
+                if (lane == 0) issue_box(bb + 2, s, dep);
             }
             while (ev < nev && PR.ev_pos[ev] < ts + ER_TILE) {   // boundaries inside the step: masked recount
                 uint32_t g[S];

@@ -92,10 +92,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_saddr, const CUtensorMa
 // lane-private bit writer: `hold` keeps the stream's last bits right-aligned (the tb & 31 bits that do not fill a word yet
 // are its lowest ones; whatever lies above is dead), `tb` counts the channel's bits.  A piece of <= 32 bits completes at
 // most one word, which goes to slot (word index & 7) of the lane's ring column.
+template <uint32_t RMASK = 7u>
 __device__ __forceinline__ void er_append(unsigned long long& hold, uint32_t& tb, uint32_t code, uint32_t len, uint32_t ring_lane) {
     hold = (hold << len) | code;
     const uint32_t tbn = tb + len;
-    if ((tbn ^ tb) & ~31u) sts_u32(ring_lane + ((tb >> 5) & 7u) * 128u, __funnelshift_r((uint32_t)hold, (uint32_t)(hold >> 32), tbn));
+    if ((tbn ^ tb) & ~31u) sts_u32(ring_lane + ((tb >> 5) & RMASK) * 128u, __funnelshift_r((uint32_t)hold, (uint32_t)(hold >> 32), tbn));
     tb = tbn;
 }
 
@@ -288,6 +289,200 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows(const __grid_c
         }
         if (!FIXED) cp_async_wait<0>();
         __syncwarp();   // everybody is done with the stages before the next block's first requests
+    }
+    signal_when_last(P);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the same for the pair encoder's codebooks (Lmax <= 8: every SCLV table up to S = 9), fixed-stride recordings
+// ---------------------------------------------------------------------------------------------
+// A lane codes its channel 64 symbols per step: the pair tables of k_encode_pair (base S+1, null digit for symbols outside the
+// window) for ALL (peak, row) pairs of the alphabet sit in shared memory (S x K x 512 B: 7.5 KB at S = 5, 103 KB at S = 9), a
+// lane addresses the one of its channel; two symbols per lookup, four lookups merged to an 8-symbol piece (<= 64 bits), pieces
+// appended by the lane-private bit writer (the upper 32 bits of a piece only when some lane's piece is that long: warp vote).
+// Rows come as TMA boxes of 64 bins x 32 channels (64-byte swizzle: piece k of row l at k ^ ((l >> 1) & 3)), two stages; the ring
+// column holds 16 words and is flushed after every 32 symbols (<= 256 bits: at most two 128-bit units).
+constexpr int ERP_STAGE = 2048;         // one box: 32 rows x 64 bytes
+constexpr int ERP_RING = 16 * 32 * 4;   // 16 words x 32 lanes
+
+struct EncRowsPairParams {
+    EncParams E;
+    int32_t wuse, warps;                // warps of a CTA that take blocks / that exist
+    uint32_t zero;
+    int32_t lut_bytes;                  // S * K * 512
+    alignas(64) CUtensorMap tmap;       // box 64 x 32, 64-byte swizzle
+};
+
+template <int SV>
+__global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows_pair(const __grid_constant__ EncRowsPairParams PR) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const EncParams& P = PR.E;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TabHdr* T = reinterpret_cast<const TabHdr*>(P.tab);
+    const int K = T->K;
+    constexpr int S = SV;
+    // shared memory: [warps x 2 stages][warps x ring][pair tables of all (peak, row) pairs][2 mbarriers per warp]
+    uint8_t* s_lut = smem_raw + (size_t)PR.warps * (2 * ERP_STAGE + ERP_RING);
+    const uint32_t lut_base = smem_u32(s_lut);
+    if (T->S != SV || S != P.S || K != P.K || T->Lmax != P.Lmax || T->Lmax > 8 || T->encp_off == 0 || (lut_base & 255u) ||
+        S * K * 512 != PR.lut_bytes) {
+        if (threadIdx.x == 0) *P.overflow = MUA_ENC_BAD_TABLE;   // launch configuration does not match the table block
+        return;
+    }
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(P.tab + T->encp_off);
+        for (int i = threadIdx.x; i < PR.lut_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_lut)[i] = g[i];
+    }
+    const uint32_t in0 = smem_u32(smem_raw) + warp * (2 * ERP_STAGE);
+    const uint32_t in_lane = (in0 + lane * 64) | (((lane >> 1) & 3) * 16);
+    const uint32_t ring_lane = smem_u32(smem_raw) + PR.warps * (2 * ERP_STAGE) + warp * ERP_RING + lane * 4;
+    const uint32_t bar0 = lut_base + PR.lut_bytes + warp * 16;
+    if (lane == 0) {
+        mbar_init(reinterpret_cast<uint64_t*>(s_lut + PR.lut_bytes) + 2 * warp, 1);
+        mbar_init(reinterpret_cast<uint64_t*>(s_lut + PR.lut_bytes) + 2 * warp + 1, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const uint32_t slot_units = (uint32_t)min((long long)(P.slot_bytes >> 4), 0x7FFFFFFFll);
+    const int nblk = (P.L.C + 31) >> 5;
+    uint32_t phase = 0;
+    constexpr uint32_t satk = (uint32_t)(0x7F - (SV - 1)) * 0x01010101u;
+    constexpr uint32_t satv = (uint32_t)(SV - 1) * 0x01010101u;
+    constexpr uint32_t nullv = (uint32_t)SV * 0x01010101u;
+    constexpr uint32_t mult = 2u | ((uint32_t)(2 * (SV + 1)) << 8);
+
+    if (warp < PR.wuse)
+    for (int blk = blockIdx.x + gridDim.x * warp; blk < nblk; blk += gridDim.x * PR.wuse) {
+        const int c = blk * 32 + lane;
+        const bool valid = c < P.L.C;
+        const int cc = valid ? c : P.L.C - 1;
+        int start = P.start[cc];
+        int end = min(P.end[cc], P.L.T);
+        const int pk_c = P.peak[cc], en_c = P.enc[cc];
+        const bool bad = pk_c >= P.S || en_c >= K;
+        if (valid && bad) *P.overflow = MUA_ENC_BAD_TABLE;
+        const bool act = valid && !bad && end > start && start >= 0;
+        const int rep_len = max(end - start, 0);
+        if (!act) { start = 0; end = 0; }
+        const uint32_t lut = lut_base + (act ? (uint32_t)(pk_c * K + en_c) * 512u : 0u);
+        uint8_t* out = P.stream + (size_t)cc * P.slot_bytes;
+        uint32_t tb = 0;
+        const int tlo = __reduce_min_sync(FULL, act ? (start & ~(ER_TILE - 1)) : 0x7FFFFFFF);
+        const int thi = __reduce_max_sync(FULL, end);
+        if (tlo < thi) {
+            const int nt = (thi - tlo + ER_TILE - 1) / ER_TILE;
+            uint32_t* co = P.chunk_off + (size_t)cc * P.chunk_stride - (start >> 10);
+            if (act) co[start >> 10] = 0;
+            auto issue_box = [&](int t, uint32_t s, uint32_t dep) {   // lane 0: box t (= step t) into stage s
+                mbar_expect_tx_s(bar0 + 8 * s, ERP_STAGE);
+                tma_load_2d(in0 + s * ERP_STAGE, &PR.tmap, tlo + ER_TILE * t + (int)dep, blk * 32, bar0 + 8 * s);
+            };
+            if (lane == 0) {
+                issue_box(0, 0, 0u);
+                if (nt > 1) issue_box(1, 1, 0u);
+            }
+            unsigned long long hold = 0;
+            int ts = tlo;
+            for (int t = 0; t < nt; ++t, ts += ER_TILE) {
+                const uint32_t s = t & 1u;
+                mbar_wait_s(bar0 + 8 * s, (phase >> s) & 1u);
+                phase ^= 1u << s;
+                const uint32_t tile = in_lane + s * ERP_STAGE;
+                uint4 qv[4];
+                uint32_t any_hi = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    qv[k] = lds_u128(tile ^ (16u * k));
+                    any_hi |= (qv[k].x | qv[k].y) | (qv[k].z | qv[k].w);
+                }
+                if (t + 2 < nt) {   // the box is in registers: its stage takes the box after the next one
+                    const uint32_t dep = any_hi & PR.zero;
+                    __syncwarp();
+                    if (lane == 0) issue_box(t + 2, s, dep);
+                }
+                if (any_hi & 0x80808080u) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) qv[k] = clamp127(qv[k]);
+                }
+                if ((ts & (TILE - 1)) == 0 && ts > start && ts < end) co[ts >> 10] = tb;
+                const bool full = __all_sync(FULL, ts >= start && ts + ER_TILE <= end);
+                const uint32_t vlo4 = (uint32_t)min(max(start - ts, 0), ER_TILE) * 0x01010101u;
+                const uint32_t vhi4 = (uint32_t)min(max(end - ts, 0), ER_TILE) * 0x01010101u;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {   // 32 symbols: four 8-symbol pieces, then the complete units leave
+                    const uint32_t tb0 = tb;
+                    unsigned long long pc[4];
+                    uint32_t pl[4], longest = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 q = qv[2 * hf + (i >> 1)];
+                        const uint32_t w2[2] = {(i & 1) ? q.z : q.x, (i & 1) ? q.w : q.y};
+                        uint32_t qc[2], ql[2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint32_t gg = w2[j] + satk;
+                            const uint32_t m = byte_msb_mask(gg);
+                            uint32_t ws = (w2[j] & ~m) | (satv & m);
+                            if (!full) {
+                                const uint32_t iv = (0x83828180u + 0x04040404u * (uint32_t)(8 * hf + 2 * i + j));   // symbol indices in the step, bit 7 set
+                                const uint32_t ok = (iv - vlo4) & ~(iv - vhi4);
+                                const uint32_t vm = byte_msb_mask(ok);
+                                ws = (ws & vm) | (nullv & ~vm);
+                            }
+                            const uint32_t prod = ws * mult;
+                            const uint32_t a0 = __byte_perm(prod, lut, 0x7651), a1 = __byte_perm(prod, lut, 0x7653);
+                            const uint32_t c0 = lds_u16(a0), l0 = lds_u8_256(a0), c1 = lds_u16(a1), l1 = lds_u8_256(a1);
+                            qc[j] = (c0 << l1) | c1;
+                            ql[j] = l0 + l1;
+                        }
+                        pc[i] = ((unsigned long long)qc[0] << ql[1]) | qc[1];
+                        pl[i] = ql[0] + ql[1];
+                        longest = max(longest, pl[i]);
+                    }
+                    const bool any_long = __any_sync(FULL, longest > 32u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t lo_len = pl[i];
+                        if (any_long) {   // rare for MUA counts: a piece of more than 32 bits goes in two parts
+                            const uint32_t hi_len = pl[i] > 32u ? pl[i] - 32u : 0u;
+                            er_append<15u>(hold, tb, hi_len ? (uint32_t)(pc[i] >> 32) : 0u, hi_len, ring_lane);
+                            lo_len = pl[i] - hi_len;
+                        }
+                        er_append<15u>(hold, tb, (uint32_t)pc[i], lo_len, ring_lane);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {   // <= 256 new bits: at most two units complete
+                        const uint32_t u = (tb0 >> 7) + r;
+                        if (u < (tb >> 7)) {
+                            const uint32_t rb = ring_lane + (u & 3u) * 512u;
+                            uint4 v4;
+                            v4.x = bswap32(lds_u32(rb)); v4.y = bswap32(lds_u32(rb + 128)); v4.z = bswap32(lds_u32(rb + 256)); v4.w = bswap32(lds_u32(rb + 384));
+                            if (u < slot_units) *reinterpret_cast<uint4*>(out + (size_t)u * 16) = v4;
+                            else *P.overflow = MUA_ENC_OVERFLOW;
+                        }
+                    }
+                }
+            }
+            if (tb & 127u) {   // last partial unit, zero padded
+                const uint32_t u = tb >> 7, nfull = tb >> 5, fill = tb & 31u;
+                const uint32_t partial = fill ? ((uint32_t)hold << (32u - fill)) : 0u;
+                uint32_t v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t wi = 4 * u + j;
+                    v[j] = wi < nfull ? lds_u32(ring_lane + (wi & 15u) * 128u) : (wi == nfull ? partial : 0u);
+                    v[j] = bswap32(v[j]);
+                }
+                if (u < slot_units) *reinterpret_cast<uint4*>(out + (size_t)u * 16) = make_uint4(v[0], v[1], v[2], v[3]);
+                else *P.overflow = MUA_ENC_OVERFLOW;
+            }
+        }
+        if (valid) {
+            P.total_bits[c] = tb;
+            const int4 rrow = make_int4((int)tb, rep_len, en_c, pk_c);
+            for (int p = 0; p < P.n_peers; ++p) *reinterpret_cast<int4*>(P.rep[p] + 4 * (P.row0 + c)) = rrow;
+        }
+        __syncwarp();
     }
     signal_when_last(P);
 }

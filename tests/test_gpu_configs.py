@@ -214,7 +214,7 @@ def test_cfg4_full_size_sweep(BP, sclv_tables):
 @pytest.mark.parametrize("T", [2400, 700])
 def test_kernel_families_agree_at_full_size(T):
     """100k short rows through BOTH kernel families (a lane per channel: k_calibrate_rows / k_encode_rows, ~22 warps per SM racing
-    their TMA boxes; a warp per channel: k_calibrate / k_encode_fast): every calibrate output, every stream byte, all side info
+    their TMA boxes; a warp per channel: k_calibrate / k_encode_fast / k_encode_pair): every calibrate output, every stream byte, all side info
     and the bit counts must be identical.  (This is the test that caught a stage refilled before a queued shared load had run.)"""
     mua_b200, P, _ = _mods()
     C = 100000
@@ -222,7 +222,7 @@ def test_kernel_families_agree_at_full_size(T):
     rec = P.synth_recording(C, T, seed=11, BP_ms=50.0, bursty=True, device=DEV)
     old = os.environ.get("MUA_ROWS_MIN_C")
     try:
-        for S in (3, 5, 10):
+        for S in (3, 5, 9, 10):
             cb = mua_b200.Codebook(S, device=DEV)
             for window in ("skip", "truncate"):
                 res = {}
@@ -230,12 +230,12 @@ def test_kernel_families_agree_at_full_size(T):
                     os.environ["MUA_ROWS_MIN_C"] = minc
                     cal = P.calibrate(rec, cb, HS, use_sort=True, window=window)
                     st, en, pk, ec = (cal[k][:, 5].contiguous() for k in ("cutoff", "end", "peak", "enc"))
-                    es = P.encode(rec, cb, st, en, pk, ec) if S == 3 else None
+                    es = P.encode(rec, cb, st, en, pk, ec)
                     res[fam] = (cal, es)
                 torch.cuda.synchronize()
                 for k in res["lanes"][0]:
                     assert torch.equal(res["lanes"][0][k], res["warps"][0][k]), (S, window, k)
-                if S == 3:
+                if True:
                     a, b = res["lanes"][1], res["warps"][1]
                     assert int(a.overflow.item()) == 0 and int(b.overflow.item()) == 0
                     assert torch.equal(a.total_bits, b.total_bits) and torch.equal(a.chunk_off, b.chunk_off)
