@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmua_b200.so")
 SOURCES = ["mua_abi.cu"]
-HEADERS = ["mua_common.cuh", "mua_calibrate.cuh", "mua_calibrate_rows.cuh", "mua_encode.cuh", "mua_encode_rows.cuh", "mua_decode.cuh", "mua_dropin.cuh",
+HEADERS = ["mua_common.cuh", "mua_calibrate.cuh", "mua_calibrate_rows.cuh", "mua_encode.cuh", "mua_encode_rows.cuh", "mua_decode.cuh", "mua_decode_rows.cuh", "mua_dropin.cuh",
            os.path.join("..", "..", "include", "mua_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
               "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]

@@ -7,6 +7,7 @@
 #include "mua_calibrate.cuh"
 #include "mua_calibrate_rows.cuh"
 #include "mua_decode.cuh"
+#include "mua_decode_rows.cuh"
 #include "mua_dropin.cuh"
 #include "mua_encode.cuh"
 #include "mua_encode_rows.cuh"
@@ -865,6 +866,25 @@ int mua_decode(const uint8_t* d_stream, int64_t slot_bytes, const uint32_t* d_ch
             cudaError_t e = cudaFuncSetAttribute(k_decode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
             k_decode_fast<false><<<grid, DF_WARPS * 32, smem, st>>>(P);
+        }
+    } else if (P.item_chunks <= 2 && C >= rows_min_channels()) {
+        // many rows whose windows span at most two chunks (the 2 400-bin rows of cfg4 at 50 ms): a lane per channel, the whole stream
+        // of a channel decoded by its lane (k_decode_rows).  Its lookup loop costs ~16 instructions per symbol against ~8 of
+        // k_decode_var, so it only pays where k_decode_var's lanes idle behind a 960- and a 240-symbol chunk per channel
+        // (100k x 2 400: S=5 0.157 -> 0.13 ms, S=9 0.39 -> 0.18 ms; 100k x 12 000: 0.31 -> 0.60 ms, not taken)
+        const int smem = DR_WARPS * DR_PER_WARP + 4 * MUA_MAX_S * 4 + h.K * ((1 << h.Wv) + DV_ROW_SKEW) * 4;
+        const long long nblk = ((long long)C + 31) / 32;
+        const int grid = (int)(nblk < sm_count() ? nblk : sm_count());
+        const long long per_sm = (nblk + grid - 1) / grid, rounds = (per_sm + DR_WARPS - 1) / DR_WARPS;
+        const int wuse = (int)((per_sm + rounds - 1) / rounds);
+        if (h.S > 8) {
+            cudaError_t e = cudaFuncSetAttribute(k_decode_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+            k_decode_rows<true><<<grid, DR_WARPS * 32, smem, st>>>(P, wuse);
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(k_decode_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "decode smem attribute");
+            k_decode_rows<false><<<grid, DR_WARPS * 32, smem, st>>>(P, wuse);
         }
     } else {
         // variable-count lookups from per-row rank tables in shared memory: one persistent CTA per SM
