@@ -61,6 +61,15 @@ def workload(a):
     if a.workload == "cfg4":
         Sx = a.alphabet
         kern = {3: ["k_calibrate<3>", "k_encode_fast<3>", "k_decode_lane"]}.get(Sx, ["k_calibrate<%d>" % Sx, "k_encode_pair<%d>" % Sx if Sx < 10 else "k_encode_gen", "k_decode_var"])
+        if a.bins <= 16384 and a.channels >= 8 * 32 * 148:
+            # many short rows: the library picks its lane-per-channel kernels (mua_abi.cu: rows_t_max / rows_min_channels)
+            kern[0] = "k_calibrate_rows<%d>" % Sx
+            if Sx <= 3:
+                kern[1] = "k_encode_rows<3,true>"
+            elif Sx < 10:
+                kern[1] = "k_encode_rows_pair<%d>" % Sx
+            if Sx > 3 and a.bins <= 2048 + 1024:
+                kern[2] = "k_decode_rows"
         return {"name": "cfg4", "S": Sx, "BP": a.bp, "T": a.bins, "H": [2 ** e for e in range(2, 11)], "h_enc": 4, "window": "skip",
                 "sclv": None, "seed": 5, "kernels": kern,
                 "want": ("cutoff", "end", "peak", "enc", "assign_m", "post_m", "bits", "nsym")}

@@ -13,7 +13,8 @@
 //     end are zero-filled by the engine, and the loads cost the SM no LSU wavefronts and no address arithmetic.
 //     (Measured on the way: a 1-D bulk copy per lane and row is bound by the TMA unit's operation rate -- ~8 cycles per
 //     operation and SM whatever its size, 2.2 TB/s for 64-byte rows; 16-byte cp.async copies spend 16-18 shared-memory
-//     wavefronts per instruction because a row's 64 bytes arrive as separate 32-byte sectors.)
+//     wavefronts per instruction because a row's 64 bytes arrive as separate 32-byte sectors; L2 prefetches ahead of the boxes --
+//     one line per lane, or a whole box by cp.async.bulk.prefetch.tensor -- made the kernel 10-30 % slower.)
 //   * ragged sets (per-channel offsets / lengths): 16-byte cp.async copies, 64 bytes per row and stage, four lanes per row and
 //     eight rows per instruction, rows padded to 80 bytes (5 x 16 B, odd: conflict-free reads);
 //   * the stream leaves the lane through a lane-private column of an 8-word ring ([word][lane]: every access conflict-free)
