@@ -171,8 +171,8 @@ int launch_calibrate_rows(const CalibParams& P, cudaStream_t st) {
         if (ev[i].is_end) PR.ev_end[ev[i].h] = i; else PR.ev_cut[ev[i].h] = i;
     }
     PR.snap_bytes = nev * (S - 1) * 64;
-    constexpr int stage = cr_box(S) * 32;
-    int warps = (227 * 1024 - CalRowsSmem::TAIL) / (2 * stage + PR.snap_bytes);
+    constexpr int stage = cr_box(S) * 32 * cr_nst(S);   // all stages of a warp
+    int warps = (227 * 1024 - CalRowsSmem::tail(cr_nst(S))) / (stage + PR.snap_bytes);
     if (warps > cr_max_warps(S)) warps = cr_max_warps(S);
     REQUIRE(warps >= 1, "calibrate: too many boundaries for shared memory");
     PR.warps = warps;
@@ -188,7 +188,7 @@ int launch_calibrate_rows(const CalibParams& P, cudaStream_t st) {
     const int grid = (int)(nblk < sm_count() ? nblk : sm_count());
     const long long per_sm = (nblk + grid - 1) / grid, rounds = (per_sm + warps - 1) / warps;
     PR.wuse = (int32_t)((per_sm + rounds - 1) / rounds);
-    const int smem = warps * (2 * stage + PR.snap_bytes) + CalRowsSmem::TAIL;
+    const int smem = warps * (stage + PR.snap_bytes) + CalRowsSmem::tail(cr_nst(S));
     cudaError_t e = cudaFuncSetAttribute(k_calibrate_rows<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "calibrate smem attribute");
     k_calibrate_rows<S><<<grid, warps * 32, smem, st>>>(PR);

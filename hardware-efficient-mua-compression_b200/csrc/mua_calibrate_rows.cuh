@@ -30,7 +30,14 @@ constexpr int CR_MAX_WARPS = 24;
 __host__ __device__ constexpr int cr_max_warps(int S) { return S <= 6 ? CR_MAX_WARPS : 16; }
 // bins per TMA box: 128 (two steps, 128-byte swizzle) while the scan is memory-bound; S > 3 count more thresholds per byte and
 // keep more counts per boundary: half-size boxes (one step, 64-byte swizzle) leave shared memory for twice the warps
-__host__ __device__ constexpr int cr_box(int S) { return S <= 3 ? 128 : 64; }
+#ifndef MUA_CR_BOX3
+#define MUA_CR_BOX3 128
+#endif
+#ifndef MUA_CR_NST3
+#define MUA_CR_NST3 2
+#endif
+__host__ __device__ constexpr int cr_box(int S) { return S <= 3 ? MUA_CR_BOX3 : 64; }
+__host__ __device__ constexpr int cr_nst(int S) { return S <= 3 ? MUA_CR_NST3 : 2; }   // stages per warp
 
 struct CalRowsParams {
     CalibParams C;
@@ -49,8 +56,8 @@ struct CalRowsSmem {                     // after the stages and the kept counts
     static constexpr int LEN = 0;                        // MUA_MAX_K x 16 B SCLV rows
     static constexpr int RANK = LEN + MUA_MAX_K * 16;    // MUA_MAX_S x 16 B rank maps
     static constexpr int HINFO = RANK + MUA_MAX_S * 16;  // int32 [4][MUA_MAX_H]: cutv, endv, ev_cut, ev_end
-    static constexpr int BARS = HINFO + 4 * MUA_MAX_H * 4;   // 2 mbarriers per warp
-    static constexpr int TAIL = BARS + CR_MAX_WARPS * 16;
+    static constexpr int BARS = HINFO + 4 * MUA_MAX_H * 4;   // one mbarrier per warp and stage
+    static constexpr int tail(int nst) { return BARS + CR_MAX_WARPS * 8 * nst; }
 };
 
 // counts of one step's 64 bytes (four 16-byte pieces in qv), bytes >= `lim` masked away: acc[v] += 0x80 per byte >= v
@@ -152,9 +159,9 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
     using SM = CalRowsSmem;
     const CalibParams& P = PR.C;
     const CalOut& O = P.out[0];
-    constexpr int BOXW = cr_box(S), SPB = BOXW / ER_TILE, STAGE = BOXW * 32;   // steps per box, bytes per stage
+    constexpr int BOXW = cr_box(S), SPB = BOXW / ER_TILE, STAGE = BOXW * 32, NST = cr_nst(S);   // steps per box, bytes per stage, stages
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* tail = smem_raw + (size_t)PR.warps * (2 * STAGE + PR.snap_bytes);
+    uint8_t* tail = smem_raw + (size_t)PR.warps * (NST * STAGE + PR.snap_bytes);
     {
         const uint4* gl = reinterpret_cast<const uint4*>(&O.tab->lens[0][0]);
         const uint4* gr = reinterpret_cast<const uint4*>(&O.tab->rank[0][0]);
@@ -168,15 +175,15 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
             hi[3 * MUA_MAX_H + threadIdx.x] = PR.ev_end[threadIdx.x];
         }
     }
-    const uint32_t in0 = smem_u32(smem_raw) + warp * (2 * STAGE);
+    const uint32_t in0 = smem_u32(smem_raw) + warp * (NST * STAGE);
     // the lane's row of stage 0 with the swizzle of its pieces folded in: 128-byte rows, piece k at 16 (k ^ (l & 7)); 64-byte rows,
     // piece k at 16 (k ^ ((l >> 1) & 3))
     const uint32_t in_lane = BOXW == 128 ? (in0 + lane * 128) | ((lane & 7) * 16) : (in0 + lane * 64) | (((lane >> 1) & 3) * 16);
-    uint16_t* snap = reinterpret_cast<uint16_t*>(smem_raw + (size_t)PR.warps * (2 * STAGE) + (size_t)warp * PR.snap_bytes);   // [e][v - 1][32 lanes]
-    const uint32_t bar0 = smem_u32(tail + SM::BARS) + warp * 16;
+    uint16_t* snap = reinterpret_cast<uint16_t*>(smem_raw + (size_t)PR.warps * (NST * STAGE) + (size_t)warp * PR.snap_bytes);   // [e][v - 1][32 lanes]
+    const uint32_t bar0 = smem_u32(tail + SM::BARS) + warp * (8 * NST);
     if (lane == 0) {
-        mbar_init(reinterpret_cast<uint64_t*>(tail + SM::BARS) + 2 * warp, 1);
-        mbar_init(reinterpret_cast<uint64_t*>(tail + SM::BARS) + 2 * warp + 1, 1);
+#pragma unroll
+        for (int i = 0; i < NST; ++i) mbar_init(reinterpret_cast<uint64_t*>(tail + SM::BARS) + NST * warp + i, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -198,8 +205,9 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
             tma_load_2d(in0 + s * STAGE, &PR.tmap, BOXW * tt + (int)dep, blk * 32, bar0 + 8 * s);
         };
         if (lane == 0) {
-            if (nbox > 0) issue_box(0, 0, 0u);
-            if (nbox > 1) issue_box(1, 1, 0u);
+#pragma unroll
+            for (int i = 0; i < NST; ++i)
+                if (i < nbox) issue_box(i, i, 0u);
         }
         // ---- scan: the lane's cumulative counts, kept at every boundary ----
         uint32_t acc[S];
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
         int ts = 0;
         for (int t = 0; t < nt; ++t, ts += ER_TILE) {
             const int bb = t / SPB, sub = t % SPB;   // box and step in the box
-            const uint32_t s = bb & 1u;
+            const uint32_t s = (uint32_t)bb % NST;
             if (sub == 0) {
                 mbar_wait_s(bar0 + 8 * s, (phase >> s) & 1u);
                 phase ^= 1u << s;
@@ -222,10 +230,10 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
             uint4 qv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) qv[k] = lds_u128(tile ^ (16u * k));
-            if (sub == SPB - 1 && bb + 2 < nbox) {   // the box is in registers: its stage takes the box after the next one
+            if (sub == SPB - 1 && bb + NST < nbox) {   // the box is in registers: its stage takes the box NST boxes on
                 const uint32_t dep = (qv[0].x | qv[1].x | qv[2].x | qv[3].x) & PR.zero;   // the four loads have been performed
                 __syncwarp();
-                if (lane == 0) issue_box(bb + 2, s, dep);
+                if (lane == 0) issue_box(bb + NST, s, dep);
             }
             while (ev < nev && PR.ev_pos[ev] < ts + ER_TILE) {   // boundaries inside the step: masked recount
                 uint32_t g[S];
