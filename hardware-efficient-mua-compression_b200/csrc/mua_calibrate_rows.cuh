@@ -55,18 +55,21 @@ struct CalRowsParams {
 struct CalRowsSmem {                     // after the stages and the kept counts of all warps:
     static constexpr int LEN = 0;                        // MUA_MAX_K x 16 B SCLV rows
     static constexpr int RANK = LEN + MUA_MAX_K * 16;    // MUA_MAX_S x 16 B rank maps
-    static constexpr int HINFO = RANK + MUA_MAX_S * 16;  // int32 [4][MUA_MAX_H]: cutv, endv, ev_cut, ev_end
+    static constexpr int SEL = RANK + MUA_MAX_S * 16;    // MUA_MAX_S x 16 B: per peak the symbols of ranks 4g..4g+3 as nibbles (PRMT selectors), g = 0..2
+    static constexpr int HINFO = SEL + MUA_MAX_S * 16;   // int32 [4][MUA_MAX_H]: cutv, endv, ev_cut, ev_end
     static constexpr int BARS = HINFO + 4 * MUA_MAX_H * 4;   // one mbarrier per warp and stage
     static constexpr int tail(int nst) { return BARS + CR_MAX_WARPS * 8 * nst; }
 };
 
 // counts of one step's 64 bytes (four 16-byte pieces in qv), bytes >= `lim` masked away: acc[v] += 0x80 per byte >= v
+// (`zz` == 0, opaque and different per boundary: without it the compiler hoists the masked recount's compare-adds, which do not
+// depend on the boundary, out of the boundary loop into EVERY step -- 90 of 231 instructions per step at S = 3)
 template <int S, bool MASKED>
-__device__ __forceinline__ void cr_count(const uint4 (&qv)[4], int lim, uint32_t (&acc)[S]) {
+__device__ __forceinline__ void cr_count(const uint4 (&qv)[4], int lim, uint32_t (&acc)[S], uint32_t zz = 0u) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (MASKED && lim <= 16 * k) break;                                     // pieces past the boundary (uniform branch)
-        const uint32_t w[4] = {qv[k].x, qv[k].y, qv[k].z, qv[k].w};
+        const uint32_t w[4] = {qv[k].x ^ zz, qv[k].y ^ zz, qv[k].z ^ zz, qv[k].w ^ zz};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t bm = 0x80808080u;
@@ -87,7 +90,7 @@ __device__ __forceinline__ void cr_count(const uint4 (&qv)[4], int lim, uint32_t
 
 // finish (channel c, history length h): gc / ge = #{x >= v} before the cutoff / the window end (index v = 1..S-1)
 template <int S>
-__device__ __forceinline__ void cr_finish(const CalibParams& P, const CalOut& O, const uint8_t* s_len, const uint8_t* s_rank, int K, int c, int h,
+__device__ __forceinline__ void cr_finish(const CalibParams& P, const CalOut& O, const uint8_t* s_len, const uint8_t* s_rank, const uint8_t* s_sel, int K, int c, int h,
                                           int cut, int end_out, int npost, bool has_post, const int (&gc)[S], const int (&ge)[S]) {
     int hist[S], post[S];
     {
@@ -121,14 +124,45 @@ __device__ __forceinline__ void cr_finish(const CalibParams& P, const CalOut& O,
         if (S <= 8) return __byte_perm(row.x, row.y, rk[s]) & 0xFFu;
         return (rk[s] < 8 ? __byte_perm(row.x, row.y, rk[s]) : __byte_perm(row.z, row.w, rk[s] - 8)) & 0xFFu;
     };
+    // SCLV costs: sum_r len[k][r] * am[r] with am = the histogram in RANK order.  The counts (< 2^16: short rows) are split into
+    // a low-byte and a high-byte plane, four symbols per word; one PRMT per word and plane (selectors = the symbols of ranks
+    // 4g..4g+3, TabHdr::idx[p], packed as nibbles) brings a plane into rank order; a cost is then 2 * ceil(S / 4) DP4As against
+    // the row's packed lengths instead of S data-dependent byte extractions and S multiply-adds
+    constexpr int NG = (S + 3) / 4;
+    uint32_t hl[3] = {0u, 0u, 0u}, hh[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        hl[s >> 2] |= ((uint32_t)hist[s] & 0xFFu) << (8 * (s & 3));
+        hh[s >> 2] |= (((uint32_t)hist[s] >> 8) & 0xFFu) << (8 * (s & 3));
+    }
+    const uint4 sel4 = *reinterpret_cast<const uint4*>(s_sel + 16 * p);
+    const uint32_t selw[3] = {sel4.x, sel4.y, sel4.z};
+    uint32_t lo[NG], hi[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (S <= 8) {
+            lo[g] = __byte_perm(hl[0], hl[1], selw[g]);
+            hi[g] = __byte_perm(hh[0], hh[1], selw[g]);
+        } else {   // symbols 8, 9 live in the third word: two PRMTs and a select by the selectors' bit 3
+            const uint32_t e7 = selw[g] & 0x7777u;
+            const uint32_t msk = __byte_perm(0x0000FF00u, 0u, (selw[g] >> 3) & 0x1111u);
+            lo[g] = (__byte_perm(hl[0], hl[1], e7) & ~msk) | (__byte_perm(hl[2], 0u, e7) & msk);
+            hi[g] = (__byte_perm(hh[0], hh[1], e7) & ~msk) | (__byte_perm(hh[2], 0u, e7) & msk);
+        }
+    }
     uint32_t best_cost = 0;
     int enc = -1;
     for (int k = 0; k < K; ++k) {   // np.argmin: first minimum (get_BR_no_sort.py:236); rows short: costs fit 32 bits
         if (!((O.active >> k) & 1ull)) continue;
         const uint4 row = *reinterpret_cast<const uint4*>(s_len + 16 * k);
-        uint32_t cost = 0;
+        const uint32_t rw[3] = {row.x, row.y, row.z};
+        uint32_t clo = 0, chi = 0;
 #pragma unroll
-        for (int s = 0; s < S; ++s) cost += (uint32_t)hist[s] * len_of(row, s);
+        for (int g = 0; g < NG; ++g) {
+            asm("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(clo) : "r"(rw[g]), "r"(lo[g]));
+            asm("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(chi) : "r"(rw[g]), "r"(hi[g]));
+        }
+        const uint32_t cost = clo + (chi << 8);
         if (enc < 0 || cost < best_cost) { best_cost = cost; enc = k; }
     }
     if (enc < 0) enc = 0;
@@ -167,6 +201,12 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
         const uint4* gr = reinterpret_cast<const uint4*>(&O.tab->rank[0][0]);
         for (int i = threadIdx.x; i < MUA_MAX_K; i += blockDim.x) reinterpret_cast<uint4*>(tail + SM::LEN)[i] = gl[i];
         if (threadIdx.x < MUA_MAX_S) reinterpret_cast<uint4*>(tail + SM::RANK)[threadIdx.x] = gr[threadIdx.x];
+        if (threadIdx.x < MUA_MAX_S) {
+            const uint8_t* ix = &O.tab->idx[threadIdx.x][0];
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int r = 0; r < 12; ++r) w[r >> 2] |= (uint32_t)(ix[r] & 0xFu) << (4 * (r & 3));
+            reinterpret_cast<uint4*>(tail + SM::SEL)[threadIdx.x] = make_uint4(w[0], w[1], w[2], 0u);
+        }
         if (threadIdx.x < MUA_MAX_H) {
             int32_t* hi = reinterpret_cast<int32_t*>(tail + SM::HINFO);
             hi[threadIdx.x] = PR.cutv[threadIdx.x];
@@ -189,6 +229,7 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
     __syncthreads();
     const uint8_t* s_len = tail + SM::LEN;
     const uint8_t* s_rank = tail + SM::RANK;
+    const uint8_t* s_sel = tail + SM::SEL;
     const int32_t* s_hinfo = reinterpret_cast<const int32_t*>(tail + SM::HINFO);
     const int K = O.tab->K;
     const int nH = P.nH;
@@ -239,7 +280,7 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
                 uint32_t g[S];
 #pragma unroll
                 for (int v = 0; v < S; ++v) g[v] = acc[v];
-                cr_count<S, true>(qv, PR.ev_pos[ev] - ts, g);
+                cr_count<S, true>(qv, PR.ev_pos[ev] - ts, g, PR.zero & (uint32_t)ev);
                 keep(ev, g);
                 ++ev;
             }
@@ -262,7 +303,7 @@ __global__ void __launch_bounds__(cr_max_warps(S) * 32, 1) k_calibrate_rows(cons
                 gc[v] = snap[(ec * (S - 1) + (v - 1)) * 32 + cl];
                 ge[v] = ee >= 0 ? snap[(ee * (S - 1) + (v - 1)) * 32 + cl] : 0;
             }
-            cr_finish<S>(P, O, s_len, s_rank, K, blk * 32 + cl, h, cut, end_out, ee >= 0 ? end_out - cut : 0, ee >= 0, gc, ge);
+            cr_finish<S>(P, O, s_len, s_rank, s_sel, K, blk * 32 + cl, h, cut, end_out, ee >= 0 ? end_out - cut : 0, ee >= 0, gc, ge);
         }
         __syncwarp();
     }
