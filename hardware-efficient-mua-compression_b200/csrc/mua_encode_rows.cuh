@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows(const __grid_c
         if (threadIdx.x == 0) *P.overflow = MUA_ENC_BAD_TABLE;   // launch configuration does not match the table block
         return;
     }
-    {   // the tables of every (peak, row) pair of this alphabet: lanes of one warp code channels with different pairs
+    {   // the tables of every (peak, row) pair of this alphabet: lanes of one warp code channels with different pairs.  (Skewing the
+        // tables against each other, as k_encode_rows_pair does, costs one LOP3 per word and gained nothing here: three tables.)
         const uint4* g_enc4 = reinterpret_cast<const uint4*>(P.tab + T->enc4_off);
         for (int i = threadIdx.x; i < S * K * (EF_LUT_B / 16); i += ER_WARPS * 32) reinterpret_cast<uint4*>(smem_raw + SM::LUT)[i] = g_enc4[i];
     }
@@ -306,6 +307,9 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows(const __grid_c
 constexpr int ERP_STAGE = 2048;         // one box: 32 rows x 64 bytes
 constexpr int ERP_RING = 16 * 32 * 4;   // 16 words x 32 lanes
 
+// bank skew of the pair table of (peak, row) pair k: its words are stored XOR-ed with this (< 32: a word stays in its 128-byte group)
+__host__ __device__ __forceinline__ uint32_t erp_skew(uint32_t k) { return (k * 5u) & 31u; }
+
 struct EncRowsPairParams {
     EncParams E;
     int32_t wuse, warps;                // warps of a CTA that take blocks / that exist
@@ -330,9 +334,14 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows_pair(const __g
         if (threadIdx.x == 0) *P.overflow = MUA_ENC_BAD_TABLE;   // launch configuration does not match the table block
         return;
     }
-    {
-        const uint4* g = reinterpret_cast<const uint4*>(P.tab + T->encp_off);
-        for (int i = threadIdx.x; i < PR.lut_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_lut)[i] = g[i];
+    {   // word w of the table of pair k goes to word w ^ erp_skew(k): the lanes of a warp code channels with DIFFERENT (peak, row)
+        // pairs, and the few hot entries (pairs of small counts) of all tables would otherwise share the same few banks
+        // (ncu at 100k x 2 400, S = 5: 64 % of the kernel's shared-memory wavefronts were bank conflicts)
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(P.tab + T->encp_off);
+        for (int i = threadIdx.x; i < PR.lut_bytes / 4; i += blockDim.x) {
+            const int k = i >> 7, w = i & 127;
+            reinterpret_cast<uint32_t*>(s_lut)[(k << 7) + (w ^ (int)erp_skew(k))] = g[i];
+        }
     }
     const uint32_t in0 = smem_u32(smem_raw) + warp * (2 * ERP_STAGE);
     const uint32_t in_lane = (in0 + lane * 64) | (((lane >> 1) & 3) * 16);
@@ -365,7 +374,9 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows_pair(const __g
         const bool act = valid && !bad && end > start && start >= 0;
         const int rep_len = max(end - start, 0);
         if (!act) { start = 0; end = 0; }
-        const uint32_t lut = lut_base + (act ? (uint32_t)(pk_c * K + en_c) * 512u : 0u);
+        const uint32_t combo = act ? (uint32_t)(pk_c * K + en_c) : 0u;
+        const uint32_t lut = lut_base + combo * 512u;
+        const uint32_t skew2 = (erp_skew(combo) * 4u) * 0x01000100u;     // the table's skew as a byte offset, at the two offset bytes of `prod`
         uint8_t* out = P.stream + (size_t)cc * P.slot_bytes;
         uint32_t tb = 0;
         const int tlo = __reduce_min_sync(FULL, act ? (start & ~(ER_TILE - 1)) : 0x7FFFFFFF);
@@ -430,7 +441,7 @@ __global__ void __launch_bounds__(ER_WARPS * 32, 1) k_encode_rows_pair(const __g
                                 const uint32_t vm = byte_msb_mask(ok);
                                 ws = (ws & vm) | (nullv & ~vm);
                             }
-                            const uint32_t prod = ws * mult;
+                            const uint32_t prod = (ws * mult) ^ skew2;
                             const uint32_t a0 = __byte_perm(prod, lut, 0x7651), a1 = __byte_perm(prod, lut, 0x7653);
                             const uint32_t c0 = lds_u16(a0), l0 = lds_u8_256(a0), c1 = lds_u16(a1), l1 = lds_u8_256(a1);
                             qc[j] = (c0 << l1) | c1;
