@@ -250,3 +250,53 @@ def test_kernel_families_agree_at_full_size(T):
             os.environ.pop("MUA_ROWS_MIN_C", None)
         else:
             os.environ["MUA_ROWS_MIN_C"] = old
+
+
+def test_fixed_stride_row_kernels_random_shapes():
+    """The TMA-box variants of the lane-per-channel kernels only see fixed-stride recordings (the randomised oracle fuzz builds
+    ragged ones): random channel counts (not multiples of 32), row lengths (not multiples of 16 / 64 / 128), arbitrary history
+    lengths, all window rules and alphabet sizes -- both kernel families must agree on every calibrate output, every stream byte,
+    the side info and the bit counts, and the lane family's streams must decode back losslessly."""
+    mua_b200, P, _ = _mods()
+    rng = np.random.default_rng(20261019)
+    old = os.environ.get("MUA_ROWS_MIN_C")
+    try:
+        for trial in range(150):
+            S = int(rng.integers(2, 11))
+            C = int(rng.choice([1, 31, 32, 33, 100, 257]))
+            T = int(rng.choice([1, 5, 63, 64, 65, 127, 129, 700, 1023, 1025, 2400, 3001]))
+            nH = int(rng.integers(1, 10))
+            HS = sorted(set(int(h) for h in rng.integers(1, 1200, size=nH)))
+            window = str(rng.choice(["skip", "truncate", "none"]))
+            use_sort = bool(rng.integers(0, 2))
+            rec = P.synth_recording(C, T, seed=100 + trial, BP_ms=float(rng.choice([10.0, 50.0])), bursty=True, device=DEV)
+            cb = mua_b200.Codebook(S, device=DEV)
+            res = {}
+            for fam, minc in (("lanes", "0"), ("warps", "2147483647")):
+                os.environ["MUA_ROWS_MIN_C"] = minc
+                cal = P.calibrate(rec, cb, HS, use_sort=use_sort, window=window)
+                h = int(rng.integers(0, len(HS))) if fam == "lanes" else res["lanes"][2]
+                st, en, pk, ec = (cal[k][:, h].contiguous() for k in ("cutoff", "end", "peak", "enc"))
+                if window == "none":
+                    en = torch.clamp(st + T // 2, max=T).to(torch.int32)
+                es = P.encode(rec, cb, st, en, pk, ec)
+                res[fam] = (cal, es, h, st, en, pk, ec)
+            torch.cuda.synchronize()
+            tag = (trial, S, C, T, HS, window, use_sort)
+            for k in res["lanes"][0]:
+                assert torch.equal(res["lanes"][0][k], res["warps"][0][k]), (tag, k)
+            a, b = res["lanes"][1], res["warps"][1]
+            assert int(a.overflow.item()) == 0 and int(b.overflow.item()) == 0, tag
+            assert torch.equal(a.total_bits, b.total_bits) and torch.equal(a.chunk_off, b.chunk_off), tag
+            used = ((a.total_bits + 127) // 128 * 16).to(torch.int64)
+            mask = torch.arange(a.slot_bytes, device=DEV)[None, :] < used[:, None]
+            assert torch.equal(a.stream.view(C, a.slot_bytes)[mask], b.stream.view(C, b.slot_bytes)[mask]), tag
+            _, es, _, st, en, pk, ec = res["lanes"]
+            os.environ["MUA_ROWS_MIN_C"] = "0"
+            dec = P.decode(es, rec, cb, st, en, pk, ec)
+            assert int(P.verify(rec, dec, S, st, en).item()) == 0, tag
+    finally:
+        if old is None:
+            os.environ.pop("MUA_ROWS_MIN_C", None)
+        else:
+            os.environ["MUA_ROWS_MIN_C"] = old
