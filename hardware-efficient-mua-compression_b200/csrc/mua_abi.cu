@@ -660,14 +660,29 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
         const int per_sm = 4;
         const int need = (C + EF_WARPS - 1) / EF_WARPS;
         const int grid = need < sm_count() * per_sm ? need : sm_count() * per_sm;
-#define MUA_LAUNCH_ENC(SV)                                                                                          \
-    do {                                                                                                            \
-        cudaError_t e = cudaFuncSetAttribute(k_encode_fast<SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                        \
-        k_encode_fast<SV><<<grid, EF_WARPS * 32, smem, st>>>(P);                                                    \
+        // fixed row stride, a multiple of 64: tiles arrive as TMA tensor boxes with the 64-byte swizzle (k_encode_fast<.., true>)
+        const bool tensor = !d_off && stride % 64 == 0 && (long long)C * stride < (1ll << 37) && tensor_map_encoder() != nullptr &&
+                            (reinterpret_cast<uintptr_t>(d_sym) & 63) == 0 && !getenv("MUA_ENC_NO_TENSOR");
+        EncFastParams PF;
+        PF.E = P;
+        memset(&PF.tmap, 0, sizeof(PF.tmap));
+        if (tensor) {
+            const cuuint64_t gdim[2] = {64, (cuuint64_t)(((long long)C * stride + 63) / 64)};
+            const cuuint64_t gstr[1] = {64};
+            const cuuint32_t box[2] = {64, 32}, estr[2] = {1, 1};
+            const CUresult r = tensor_map_encoder()(&PF.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(d_sym), gdim, gstr, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        }
+#define MUA_LAUNCH_ENC(SV, TN)                                                                                          \
+    do {                                                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(k_encode_fast<SV, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                            \
+        k_encode_fast<SV, TN><<<grid, EF_WARPS * 32, smem, st>>>(PF);                                                   \
     } while (0)
-        if (S == 2) MUA_LAUNCH_ENC(2);
-        else MUA_LAUNCH_ENC(3);
+        if (S == 2) { if (tensor) MUA_LAUNCH_ENC(2, true); else MUA_LAUNCH_ENC(2, false); }
+        else { if (tensor) MUA_LAUNCH_ENC(3, true); else MUA_LAUNCH_ENC(3, false); }
 #undef MUA_LAUNCH_ENC
     } else if (h.Lmax <= 8 && S >= 3 && S <= 9 && T > 0 && T <= rows_t_max() && C >= rows_min_channels() && !d_off && !d_len &&
                tensor_map_encoder() != nullptr && (227 * 1024 - S * K * 512) / (2 * ERP_STAGE + ERP_RING + 16) >= 8) {

@@ -12,6 +12,8 @@
 //                   the window, 8-symbol pieces OR-ed into a zeroed ring with shared-memory atomics.
 //   k_encode_gen  : any codebook (Lmax <= 9): nibble-pair LUT + sequential per-lane bit writer.
 #pragma once
+#include <cuda.h>
+
 #include "mua_common.cuh"
 
 namespace mua {
@@ -76,6 +78,19 @@ __device__ __forceinline__ void signal_when_last(const EncParams& P) {
                 asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(P.flags[threadIdx.x] + P.rank), "r"(P.signal_step) : "memory");
         }
     }
+}
+
+// k_encode_fast with the recording described to the TMA engine (see there)
+struct EncFastParams {
+    EncParams E;
+    alignas(64) CUtensorMap tmap;   // TENSOR: the recording's bytes as uint8 [bytes / 64][64], box 64 x 32 (one 2048-symbol tile), 64-byte swizzle
+};
+
+__device__ __forceinline__ void tma_load_2d_p(void* dst_smem, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 constexpr int ENC_WARPS = 8;
@@ -259,9 +274,12 @@ __device__ __forceinline__ uint4 clamp127(uint4 q) {
 }
 
 // The four 16-symbol pieces of a lane in a full tile.  The lane's 64 bytes are four 16-byte pieces; with a lane stride
-// of 64 bytes, reading piece k in every lane would be a bank conflict, so lane l reads piece (k + rot) mod 4 (rot from the
-// lane index: conflict-free) and a two-level select network puts the results back in order.
-template <int SV>
+// of 64 bytes, reading piece k in every lane would be a bank conflict.
+//   TENSOR: the tile was written by a TMA tensor box with the 64-byte swizzle (piece k of lane l at k ^ ((l >> 1) & 3)): the lane
+//           reads its pieces in order, conflict-free, and codes them in order;
+//   else  : lane l reads piece (k + rot) mod 4 (rot from the lane index: conflict-free) and a two-level select network puts the
+//           results back in order (16 SEL + the rotation arithmetic per tile, on the ALU pipe that bounds the kernel).
+template <int SV, bool TENSOR>
 __device__ __forceinline__ void enc_fast_pieces(const uint8_t* tile, uint32_t lut_saddr, int lane, uint32_t (&pc)[4], uint32_t (&pl)[4]) {
     constexpr int NP = 4;
     const uint32_t rot = (lane >> 1) & 3;
@@ -269,7 +287,7 @@ __device__ __forceinline__ void enc_fast_pieces(const uint8_t* tile, uint32_t lu
     uint32_t any_hi = 0;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-        qv[k] = *reinterpret_cast<const uint4*>(tile + 16 * ((k + rot) & (NP - 1)));
+        qv[k] = TENSOR ? *reinterpret_cast<const uint4*>(tile + 16 * (k ^ rot)) : *reinterpret_cast<const uint4*>(tile + 16 * ((k + rot) & (NP - 1)));
         any_hi |= (qv[k].x | qv[k].y) | (qv[k].z | qv[k].w);
     }
     if (__any_sync(FULL, (any_hi & 0x80808080u) != 0)) {   // rare: a count >= 128 somewhere in the tile
@@ -278,20 +296,22 @@ __device__ __forceinline__ void enc_fast_pieces(const uint8_t* tile, uint32_t lu
     }
 #pragma unroll
     for (int k = 0; k < NP; ++k) encode16<SV>(qv[k], lut_saddr, pc[k], pl[k]);
+    if (!TENSOR) {
 #pragma unroll
-    for (int lev = 1; lev < NP; lev <<= 1) {
-        const bool r = rot & lev;
-        uint32_t tc[NP], tl4[NP];
+        for (int lev = 1; lev < NP; lev <<= 1) {
+            const bool r = rot & lev;
+            uint32_t tc[NP], tl4[NP];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) { tc[j] = r ? pc[(j - lev) & (NP - 1)] : pc[j]; tl4[j] = r ? pl[(j - lev) & (NP - 1)] : pl[j]; }
+            for (int j = 0; j < NP; ++j) { tc[j] = r ? pc[(j - lev) & (NP - 1)] : pc[j]; tl4[j] = r ? pl[(j - lev) & (NP - 1)] : pl[j]; }
 #pragma unroll
-        for (int j = 0; j < NP; ++j) { pc[j] = tc[j]; pl[j] = tl4[j]; }
+            for (int j = 0; j < NP; ++j) { pc[j] = tc[j]; pl[j] = tl4[j]; }
+        }
     }
 }
 
 // The pieces of a lane in a partial tile: lane l holds symbols [16 k l, 16 k (l + 1)) of the tile, k = pieces per lane (1..4,
 // warp-uniform); symbols outside the window code no bits; pieces >= k are empty.
-template <int SV>
+template <int SV, bool TENSOR>
 __device__ __forceinline__ void enc_fast_pieces_partial(const uint8_t* tile_w, uint32_t lutn_saddr, int ts, int start, int end, int k, int lane,
                                                         uint32_t (&pc)[4], uint32_t (&pl)[4]) {
     const uint8_t* lp = tile_w + lane * 16 * k;
@@ -304,7 +324,12 @@ __device__ __forceinline__ void enc_fast_pieces_partial(const uint8_t* tile_w, u
     for (int i = 0; i < 4; ++i) {
         qv[i] = make_uint4(0, 0, 0, 0);
         if (i < k) {
-            qv[i] = *reinterpret_cast<const uint4*>(lp + 16 * i);
+            if (TENSOR) {   // swizzled tile: the piece at byte offset o sits in row o / 64 at chunk (o / 16 % 4) ^ (row / 2 % 4)
+                const uint32_t o = (uint32_t)(lane * 16 * k + 16 * i);
+                qv[i] = *reinterpret_cast<const uint4*>(tile_w + ((o & ~63u) | ((((o >> 4) ^ (o >> 7)) & 3u) << 4)));
+            } else {
+                qv[i] = *reinterpret_cast<const uint4*>(lp + 16 * i);
+            }
             any_hi |= (qv[i].x | qv[i].y) | (qv[i].z | qv[i].w);
         }
     }
@@ -378,8 +403,14 @@ __device__ __forceinline__ void enc_fast_place(const uint32_t (&pc)[4], const ui
     Pbits = Pnew;
 }
 
-template <int SV>   // alphabet size as a compile-time constant: the SWAR constants and the gather multipliers are immediates
-__global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_constant__ EncParams P) {
+// TENSOR (fixed row stride, a multiple of 64): a tile is ONE TMA tensor box -- the recording's bytes as a 2-D tensor of 64-byte
+// rows, box 64 x 32 = the tile's 2048 bytes, 64-byte swizzle -- instead of a 1-D bulk copy: the hardware swizzle makes the lanes'
+// reads of their 64 bytes conflict-free IN ORDER, which removes the rotated reads and the select network that undoes them
+// (~23 of the tile's 232 ALU-pipe instructions; the kernel is bound by that pipe).  Bytes past the end of the buffer are zero-filled
+// by the engine, bytes past the window are masked by the null digit as before.
+template <int SV, bool TENSOR>   // alphabet size as a compile-time constant: the SWAR constants and the gather multipliers are immediates
+__global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_constant__ EncFastParams PF) {
+    const EncParams& P = PF.E;
     static_assert(SV == 2 || SV == 3, "the null-digit table needs (S+1)^4 <= 256 entries");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = EncFastSmem;
@@ -428,7 +459,8 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
                 cur_combo = combo;
                 __syncwarp();
             }
-            const uint8_t* row = P.L.sym + ch_off(P.L, c);
+            const int64_t row_off = ch_off(P.L, c);
+            const uint8_t* row = P.L.sym + row_off;
             const int A0 = start & ~63;                   // tiles start with the window (rounded down to a lane's 64 symbols)
             const int nt = (end - A0 + ETILE - 1) / ETILE;
             const int rd_end = (end + 15) & ~15;
@@ -458,9 +490,14 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
                 const int npro = nt < EF_NST ? nt : EF_NST;
                 for (int t = 0; t < npro; ++t) {
                     const int ts = A0 + t * ETILE;
-                    const uint32_t bytes = (uint32_t)min(ETILE, rd_end - ts);
-                    mbar_expect_tx(&s_bar[s2], bytes);
-                    tma_load_1d(s_in + s2 * ETILE, row + ts, bytes, &s_bar[s2]);
+                    if (TENSOR) {
+                        mbar_expect_tx(&s_bar[s2], ETILE);
+                        tma_load_2d_p(s_in + s2 * ETILE, &PF.tmap, 0, (int)((row_off + ts) >> 6), &s_bar[s2]);
+                    } else {
+                        const uint32_t bytes = (uint32_t)min(ETILE, rd_end - ts);
+                        mbar_expect_tx(&s_bar[s2], bytes);
+                        tma_load_1d(s_in + s2 * ETILE, row + ts, bytes, &s_bar[s2]);
+                    }
                     s2 = (s2 + 1) & (EF_NST - 1);
                 }
             }
@@ -473,14 +510,14 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
                 uint32_t a_lane, pc[4], pl[4];
                 const bool full = (ts >= start) && (ts + ETILE <= end);       // warp-uniform
                 if (full) {
-                    enc_fast_pieces<SV>(tile_w + lane * 64, lut_saddr, lane, pc, pl);
+                    enc_fast_pieces<SV, TENSOR>(tile_w + lane * 64, lut_saddr, lane, pc, pl);
                     enc_fast_place<true, RM>(pc, pl, lane, s_ring, Pbits, carry, a_lane);
                     if ((int)co_b >= 0) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(P.chunk_off) + (co_b + 8u * (uint32_t)t)) = a_lane;
                     if ((int)so_b >= 0) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(P.sub_off) + (so_b + 64u * (uint32_t)t)) = a_lane;
                 } else {
                     // partial tile: k 16-symbol pieces per lane cover what is left of the window
                     const int k = min(4, (end - ts + 511) >> 9);
-                    enc_fast_pieces_partial<SV>(tile_w, lut_saddr + 256, ts, start, end, k, lane, pc, pl);
+                    enc_fast_pieces_partial<SV, TENSOR>(tile_w, lut_saddr + 256, ts, start, end, k, lane, pc, pl);
                     enc_fast_place<false, RM>(pc, pl, lane, s_ring, Pbits, carry, a_lane);
                     // chunk offsets: the (at most two) absolute multiples of 1024 inside the tile and strictly inside the window
                     const uint32_t kinv = k == 4 ? 64u : (k == 3 ? 86u : (k == 2 ? 128u : 256u));   // floor(pi / k) = pi * kinv >> 8 for pi < 128
@@ -519,9 +556,14 @@ __global__ void __launch_bounds__(EF_WARPS * 32, 4) k_encode_fast(const __grid_c
                 __syncwarp();
                 if (lane == 0 && t + EF_NST < nt) {
                     const int ts2 = ts + EF_NST * ETILE;
-                    const uint32_t bytes = (uint32_t)min(ETILE, rd_end - ts2);
-                    mbar_expect_tx(&s_bar[slot], bytes);
-                    tma_load_1d(s_in + slot * ETILE, row + ts2, bytes, &s_bar[slot]);
+                    if (TENSOR) {
+                        mbar_expect_tx(&s_bar[slot], ETILE);
+                        tma_load_2d_p(s_in + slot * ETILE, &PF.tmap, 0, (int)((row_off + ts2) >> 6), &s_bar[slot]);
+                    } else {
+                        const uint32_t bytes = (uint32_t)min(ETILE, rd_end - ts2);
+                        mbar_expect_tx(&s_bar[slot], bytes);
+                        tma_load_1d(s_in + slot * ETILE, row + ts2, bytes, &s_bar[slot]);
+                    }
                 }
                 slot = (slot + 1) & (EF_NST - 1);
                 parity ^= (slot == 0);
