@@ -60,7 +60,7 @@ def workload(a):
     """the two bench workloads as data: alphabet, history lengths, window rule, SCLV rows, kernels of a step"""
     if a.workload == "cfg4":
         Sx = a.alphabet
-        kern = {3: ["k_calibrate<3>", "k_encode_fast<3>", "k_decode_lane"]}.get(Sx, ["k_calibrate<%d>" % Sx, "k_encode_pair<%d>" % Sx if Sx < 10 else "k_encode_gen", "k_decode_var"])
+        kern = {3: ["k_calibrate<3>", "k_encode_fast<3,tensor>", "k_decode_lane"]}.get(Sx, ["k_calibrate<%d>" % Sx, "k_encode_pair<%d>" % Sx if Sx < 10 else "k_encode_gen", "k_decode_var"])
         if a.bins <= 16384 and a.channels >= 8 * 32 * 148:
             # many short rows: the library picks its lane-per-channel kernels (mua_abi.cu: rows_t_max / rows_min_channels)
             kern[0] = "k_calibrate_rows<%d>" % Sx
@@ -74,7 +74,7 @@ def workload(a):
                 "sclv": None, "seed": 5, "kernels": kern,
                 "want": ("cutoff", "end", "peak", "enc", "assign_m", "post_m", "bits", "nsym")}
     return {"name": "cfg5", "S": S, "BP": BP, "T": a.bins, "H": [H], "h_enc": 0, "window": "truncate", "sclv": np.array([SCLV]),
-            "seed": SEED, "kernels": ["k_calibrate_head<3,4>", "k_encode_fast<3>", "k_decode_lane<1>"],
+            "seed": SEED, "kernels": ["k_calibrate_head<3,4>", "k_encode_fast<3,tensor>", "k_decode_lane<1>"],
             "want": ("cutoff", "end", "peak", "enc")}
 
 
