@@ -16,6 +16,10 @@
  *     uploaded from the caller's stack frame).
  *   - return value: 0 = ok, <0 = error (MUA_E_*); mua_last_error() returns a thread-local message.
  *   - re-entrant across distinct streams/devices.
+ *   - kernel choice: mua_calibrate / mua_encode / mua_decode pick between two kernel families by the shape of the recording (a warp
+ *     per channel; a lane per channel for recordings of many short rows) -- results are identical.  Three
+ *     environment variables override the choice for A/B measurements and tests (MUA_ROWS_MIN_C, MUA_ROWS_T, MUA_ENC_NO_TENSOR);
+ *     nothing else is read from the environment.
  *
  * Channel layout ("recording"): symbols are uint8, one row per channel:
  *     channel c occupies d_sym[off(c) .. off(c)+len(c)),  off(c) = d_off ? d_off[c] : c*stride,
