@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised differential test of the whole path against the oracle (GPU box): random alphabet size, codebook
-(canonical or the generator's codewords), SCLV row subset, history lengths, window rule, sort mode and ragged
-recordings; every calibrate output, every stream byte, every chunk offset and the decoded symbols are compared.
+(canonical or the generator's codewords), SCLV row subset, history lengths, window rule, sort mode, ragged and
+fixed-stride recordings; every calibrate output, every stream byte, every chunk offset and the decoded symbols are compared.
 
   python tests/fuzz_parity.py [seconds=120] [seed=0]        prints one JSON line; exit code 1 on the first mismatch"""
 import json
@@ -30,7 +30,7 @@ def one_trial(rng, tables):
     nch = int(rng.integers(1, 33))
     special = [0, 1, 2, 15, 16, 17, 63, 64, 65, 1023, 1024, 1025, 2047, 2048, 2049, 4096]
     lens = [int(rng.choice(special)) if rng.random() < 0.25 else int(rng.integers(1, 6000)) for _ in range(nch)]
-    if rng.random() < 0.3:
+    if rng.random() < 0.45:
         lens = [lens[0] or 100] * nch                                   # uniform layout
     chans = []
     for n in lens:
@@ -41,7 +41,10 @@ def one_trial(rng, tables):
         chans.append(x)
     if all(len(x) == 0 for x in chans):
         chans[0] = rng.poisson(1.0, size=50).astype(np.uint8)
-    rec = P.Recording.from_channels(chans, DEV)
+    if len(set(len(x) for x in chans)) == 1 and len(chans[0]) > 0 and rng.random() < 0.7:
+        rec = P.Recording.from_matrix(np.stack(chans), DEV)             # fixed stride: the TMA-box variants of the row kernels
+    else:
+        rec = P.Recording.from_channels(chans, DEV)
     if rng.random() < 0.5:
         HS = sorted(set(int(h) for h in rng.choice(O.HIST_SIZES, size=int(rng.integers(1, 10)), replace=True)))
     else:
