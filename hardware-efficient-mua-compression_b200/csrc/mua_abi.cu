@@ -726,11 +726,30 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
     } else if (h.Lmax <= 8 && S >= 3 && S <= 9) {
         const int smem = EncPairSmem::PER_WARP * ENC_WARPS;
         const int grid = ctas_needed < sm_count() * 3 ? ctas_needed : sm_count() * 3;
-#define MUA_LAUNCH_ENCP(SV)                                                                                         \
-    do {                                                                                                            \
-        cudaError_t e = cudaFuncSetAttribute(k_encode_pair<SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                        \
-        k_encode_pair<SV><<<grid, ENC_WARPS * 32, smem, st>>>(P);                                                   \
+        const bool tensor = !d_off && stride % 64 == 0 && (long long)C * stride < (1ll << 37) && tensor_map_encoder() != nullptr &&
+                            (reinterpret_cast<uintptr_t>(d_sym) & 63) == 0 && !getenv("MUA_ENC_NO_TENSOR");
+        EncFastParams PF;
+        PF.E = P;
+        memset(&PF.tmap, 0, sizeof(PF.tmap));
+        if (tensor) {   // the recording's bytes as 64-byte rows, one box of 64 x 32 per 2048-symbol tile (see k_encode_fast)
+            const cuuint64_t gdim[2] = {64, (cuuint64_t)(((long long)C * stride + 63) / 64)};
+            const cuuint64_t gstr[1] = {64};
+            const cuuint32_t box[2] = {64, 32}, estr[2] = {1, 1};
+            const CUresult r = tensor_map_encoder()(&PF.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(d_sym), gdim, gstr, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        }
+#define MUA_LAUNCH_ENCP1(SV, TN)                                                                                        \
+    do {                                                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(k_encode_pair<SV, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "encode smem attribute");                                            \
+        k_encode_pair<SV, TN><<<grid, ENC_WARPS * 32, smem, st>>>(PF);                                                  \
+    } while (0)
+#define MUA_LAUNCH_ENCP(SV)                                \
+    do {                                                   \
+        if (tensor) MUA_LAUNCH_ENCP1(SV, true);            \
+        else MUA_LAUNCH_ENCP1(SV, false);                  \
     } while (0)
         switch (S) {
             case 3: MUA_LAUNCH_ENCP(3); break;
@@ -741,6 +760,7 @@ int mua_encode(const uint8_t* d_sym, const int64_t* d_off, const int32_t* d_len,
             case 8: MUA_LAUNCH_ENCP(8); break;
             default: MUA_LAUNCH_ENCP(9); break;
         }
+#undef MUA_LAUNCH_ENCP1
 #undef MUA_LAUNCH_ENCP
     } else {
         const int smem = EncGenSmem::PER_WARP * ENC_WARPS;

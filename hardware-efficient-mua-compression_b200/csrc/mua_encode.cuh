@@ -812,7 +812,10 @@ __device__ __forceinline__ void flush_units_z(uint32_t* s_ring, uint8_t* out, ui
 
 // One 2048-symbol tile: lane l codes symbols [32l, 32l+32) of each of the tile's two chunks.  Returns the bit
 // count of the first chunk (the second chunk's offset).
-template <int SV, bool FULLT, uint32_t RM>
+// TENSOR: `tile` is the stage base and the tile was written by a TMA tensor box with the 64-byte swizzle (see k_encode_fast): the 16-byte
+// piece at byte offset o sits in row o / 64 at chunk (o / 16 % 4) ^ (row / 2 % 4), which makes the lanes' reads at a 32-byte lane stride
+// conflict-free (linear layout: two-way conflicts); else `tile` is the lane's first byte of a linear tile.
+template <int SV, bool FULLT, uint32_t RM, bool TENSOR>
 __device__ __forceinline__ uint32_t enc_pair_tile(const uint8_t* tile, uint32_t lutp_saddr, int ts, int start, int end, int lane,
                                                   uint32_t* s_ring, uint32_t& Pbits) {
     constexpr uint32_t satk = (uint32_t)(0x7F - (SV - 1)) * 0x01010101u;
@@ -823,8 +826,15 @@ __device__ __forceinline__ uint32_t enc_pair_tile(const uint8_t* tile, uint32_t 
     uint32_t any_hi = 0;
 #pragma unroll
     for (int g = 0; g < EP_NG; ++g) {
-        q[2 * g] = *reinterpret_cast<const uint4*>(tile + g * TILE);
-        q[2 * g + 1] = *reinterpret_cast<const uint4*>(tile + g * TILE + 16);
+        if (TENSOR) {   // row = 16 g + lane / 2 (row / 2 % 4 == lane / 4 % 4), chunks 2 (lane & 1) and 2 (lane & 1) + 1
+            const uint8_t* rowp = tile + g * TILE + (lane >> 1) * 64;
+            const int sw = (lane >> 2) & 3, c0 = 2 * (lane & 1);
+            q[2 * g] = *reinterpret_cast<const uint4*>(rowp + ((c0 ^ sw) << 4));
+            q[2 * g + 1] = *reinterpret_cast<const uint4*>(rowp + (((c0 + 1) ^ sw) << 4));
+        } else {
+            q[2 * g] = *reinterpret_cast<const uint4*>(tile + g * TILE);
+            q[2 * g + 1] = *reinterpret_cast<const uint4*>(tile + g * TILE + 16);
+        }
         any_hi |= (q[2 * g].x | q[2 * g].y) | (q[2 * g].z | q[2 * g].w) | (q[2 * g + 1].x | q[2 * g + 1].y) | (q[2 * g + 1].z | q[2 * g + 1].w);
     }
     if (__any_sync(FULL, (any_hi & 0x80808080u) != 0)) {   // rare: a count >= 128 somewhere in the tile
@@ -928,8 +938,9 @@ __device__ __forceinline__ uint32_t enc_pair_tile(const uint8_t* tile, uint32_t 
     return tot0;
 }
 
-template <int SV>
-__global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_constant__ EncParams P) {
+template <int SV, bool TENSOR>   // TENSOR: tiles as TMA tensor boxes with the 64-byte swizzle (row stride a multiple of 64), as in k_encode_fast
+__global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_constant__ EncFastParams PF) {
+    const EncParams& P = PF.E;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     using SM = EncPairSmem;
     constexpr uint32_t RM = SM::RW - 1;
@@ -976,7 +987,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
                 cur_combo = combo;
                 __syncwarp();
             }
-            const uint8_t* row = P.L.sym + ch_off(P.L, c);
+            const int64_t row_off = ch_off(P.L, c);
+            const uint8_t* row = P.L.sym + row_off;
             const int A0 = start & ~(EP_TILE - 1);
             const int nt = (end - A0 + EP_TILE - 1) / EP_TILE;
             const int rd_end = (end + 15) & ~15;
@@ -989,9 +1001,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
                 const int npro = nt < EP_NST ? nt : EP_NST;
                 for (int t = 0; t < npro; ++t) {
                     const int ts = A0 + t * EP_TILE;
-                    const uint32_t bytes = (uint32_t)min(EP_TILE, rd_end - ts);
-                    mbar_expect_tx(&s_bar[s2], bytes);
-                    tma_load_1d(s_in + s2 * EP_TILE, row + ts, bytes, &s_bar[s2]);
+                    if (TENSOR) {
+                        mbar_expect_tx(&s_bar[s2], EP_TILE);
+                        tma_load_2d_p(s_in + s2 * EP_TILE, &PF.tmap, 0, (int)((row_off + ts) >> 6), &s_bar[s2]);
+                    } else {
+                        const uint32_t bytes = (uint32_t)min(EP_TILE, rd_end - ts);
+                        mbar_expect_tx(&s_bar[s2], bytes);
+                        tma_load_1d(s_in + s2 * EP_TILE, row + ts, bytes, &s_bar[s2]);
+                    }
                     s2 = (s2 + 1) & (EP_NST - 1);
                 }
             }
@@ -999,12 +1016,12 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
             int ts = A0;
             for (int t = 0; t < nt; ++t, ts += EP_TILE) {
                 mbar_wait(&s_bar[slot], parity);
-                const uint8_t* tile = s_in + slot * EP_TILE + lane * 32;
+                const uint8_t* tile = s_in + slot * EP_TILE + (TENSOR ? 0 : lane * 32);
                 const uint32_t Pold = Pbits;
                 const bool full = (ts >= start) && (ts + EP_TILE <= end);    // warp-uniform
                 uint32_t tot0;
-                if (full) tot0 = enc_pair_tile<SV, true, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
-                else tot0 = enc_pair_tile<SV, false, RM>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
+                if (full) tot0 = enc_pair_tile<SV, true, RM, TENSOR>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
+                else tot0 = enc_pair_tile<SV, false, RM, TENSOR>(tile, lutp_saddr, ts, start, end, lane, s_ring, Pbits);
                 if (lane < EP_NG) {
                     const int cs = ts + lane * TILE;                         // absolute start of that chunk
                     if (cs + TILE > start && cs < end) co[EP_NG * t + lane] = Pold + (lane ? tot0 : 0u);
@@ -1015,9 +1032,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 3) k_encode_pair(const __grid_
                 __syncwarp();
                 if (lane == 0 && t + EP_NST < nt) {
                     const int ts2 = ts + EP_NST * EP_TILE;
-                    const uint32_t bytes = (uint32_t)min(EP_TILE, rd_end - ts2);
-                    mbar_expect_tx(&s_bar[slot], bytes);
-                    tma_load_1d(s_in + slot * EP_TILE, row + ts2, bytes, &s_bar[slot]);
+                    if (TENSOR) {
+                        mbar_expect_tx(&s_bar[slot], EP_TILE);
+                        tma_load_2d_p(s_in + slot * EP_TILE, &PF.tmap, 0, (int)((row_off + ts2) >> 6), &s_bar[slot]);
+                    } else {
+                        const uint32_t bytes = (uint32_t)min(EP_TILE, rd_end - ts2);
+                        mbar_expect_tx(&s_bar[slot], bytes);
+                        tma_load_1d(s_in + slot * EP_TILE, row + ts2, bytes, &s_bar[slot]);
+                    }
                 }
                 slot = (slot + 1) & (EP_NST - 1);
                 parity ^= (slot == 0);
